@@ -1,0 +1,20 @@
+"""picha_b200 -- B200-native implementation of jhs67/picha's pixel hot path.
+
+The product is ``libpicha_b200.so`` (hand-written sm_100a kernels behind the C-ABI of
+include/picha_b200.h).  This package is the host-side mirror of picha's JS surface for that
+path -- ``Image`` (lib/image.js) and ``resize`` / ``resizeSync`` / ``colorConvert`` /
+``colorConvertSync`` (index.js:13-33) -- plus the device-resident batch helpers the
+benchmark uses.  Importing it requires the built library; there is no CPU fallback.
+"""
+from ._native import EXACT, FILTERS, PIXELS, PichaError, lib   # noqa: F401
+from .api import (colorConvert, colorConvertBatchSync, colorConvertSync, resize,   # noqa: F401
+                  resizeBatchSync, resizeSync)
+from .image import Image   # noqa: F401
+
+
+def device_count():
+    return lib.picha_b200_device_count()
+
+
+def launch_count():
+    return lib.picha_b200_launch_count()

@@ -1,0 +1,676 @@
+// C-ABI layer (include/picha_b200.h): validation with the reference's error behaviour, device
+// selection, per-thread-safe lanes (stream + pinned staging + device scratch), the resize plan
+// cache, host batches pipelined over streams and sharded over GPUs, and the device entry points.
+//
+// Reference seams replaced here:
+//   resizeImage(const ResizeOptions&, NativeImage&, NativeImage&)      src/resize.cc:270-280
+//   doColorConvert(const ColorSettings&, NativeImage&, NativeImage&)   src/colorconvert.cc:171-188
+// and the checks their NAN callers make before reaching them (src/resize.cc:321-403,
+// src/colorconvert.cc:215-291, src/picha.cc:61-85).
+#include "../../include/picha_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+#include "kernels.h"
+#include "tables.h"
+
+namespace picha_b200 {
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_default_device{-1};   // -1: not chosen yet (env PICHA_B200_DEVICE or 0)
+
+int fail_cuda(cudaError_t e, const char *what) {
+	g_last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+	cudaGetLastError();   // clear the sticky-free error state
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+		return PICHA_B200_ERR_NO_DEVICE;
+	if (e == cudaErrorMemoryAllocation) return PICHA_B200_ERR_NOMEM;
+	return PICHA_B200_ERR_CUDA;
+}
+#define CU(call)                                              \
+	do {                                                      \
+		cudaError_t e_ = (call);                              \
+		if (e_ != cudaSuccess) return fail_cuda(e_, #call);   \
+	} while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- grow-only buffers -----------------------------------------------------------------
+
+struct PinnedBuf {
+	uint8_t *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n) {
+		if (n <= cap) return 0;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = align_up(n + n / 4, 1 << 20);
+		CU(cudaHostAlloc((void **)&p, want, cudaHostAllocPortable));
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct DeviceBuf {
+	uint8_t *p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t n) {
+		if (n <= cap) return 0;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = align_up(n + n / 4, 1 << 20);
+		CU(cudaMalloc((void **)&p, want));
+		cap = want;
+		return 0;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ---- resize plans ------------------------------------------------------------------------
+
+struct Plan {
+	AxisTable x, y;
+	uint32_t *blob = nullptr;   // device
+	ResizeTables t{};
+	~Plan() { if (blob) cudaFree(blob); }
+};
+
+typedef std::tuple<int, uint32_t, int, int, int, int> PlanKey;   // filter, width bits, sw, sh, dw, dh
+
+// A lane is what one in-flight host call owns: a stream, staging and device scratch.
+struct Lane {
+	cudaStream_t stream = nullptr;
+	PinnedBuf hin, hout;
+	DeviceBuf din, dout;
+	// pending copy-out of a staged result (batch pipelining)
+	const picha_b200_image *pending_dst = nullptr;
+	size_t pending_pitch = 0;
+};
+
+struct Device {
+	int id = 0;
+	int smem_optin = 0;
+	std::mutex mu;
+	std::vector<Lane *> idle;
+	std::vector<Lane *> all;
+	std::map<PlanKey, std::shared_ptr<Plan>> plans;
+	std::list<PlanKey> lru;
+
+	Lane *acquire() {
+		{
+			std::lock_guard<std::mutex> g(mu);
+			if (!idle.empty()) { Lane *l = idle.back(); idle.pop_back(); return l; }
+		}
+		Lane *l = new Lane();
+		if (cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) != cudaSuccess) { delete l; return nullptr; }
+		std::lock_guard<std::mutex> g(mu);
+		all.push_back(l);
+		return l;
+	}
+	void release(Lane *l) {
+		std::lock_guard<std::mutex> g(mu);
+		idle.push_back(l);
+	}
+};
+
+std::mutex g_devices_mu;
+std::vector<Device *> g_devices;   // index = CUDA ordinal
+int g_device_count = -1;
+
+int device_count() {
+	std::lock_guard<std::mutex> g(g_devices_mu);
+	if (g_device_count < 0) {
+		int n = 0;
+		cudaError_t e = cudaGetDeviceCount(&n);
+		if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+		g_device_count = n;
+		g_devices.assign(n, nullptr);
+	}
+	return g_device_count;
+}
+
+Device *get_device(int ordinal) {
+	int n = device_count();
+	if (ordinal < 0 || ordinal >= n) return nullptr;
+	std::lock_guard<std::mutex> g(g_devices_mu);
+	if (!g_devices[ordinal]) {
+		Device *d = new Device();
+		d->id = ordinal;
+		cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ordinal);
+		g_devices[ordinal] = d;
+	}
+	return g_devices[ordinal];
+}
+
+int default_ordinal() {
+	int d = g_default_device.load();
+	if (d >= 0) return d;
+	const char *env = getenv("PICHA_B200_DEVICE");
+	return env ? atoi(env) : 0;
+}
+
+// Build (or fetch) the plan for one resize shape on `dev`. The current CUDA device must be dev->id.
+int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, std::shared_ptr<Plan> *out) {
+	uint32_t wbits;
+	memcpy(&wbits, &width, 4);
+	PlanKey key(tag, wbits, sw, sh, dw, dh);
+	std::lock_guard<std::mutex> g(dev->mu);
+	auto it = dev->plans.find(key);
+	if (it != dev->plans.end()) {
+		dev->lru.remove(key);
+		dev->lru.push_front(key);
+		*out = it->second;
+		return 0;
+	}
+	std::shared_ptr<Plan> p(new Plan());
+	build_axis(tag, width, sw, dw, p->x);
+	build_axis(tag, width, sh, dh, p->y);
+
+	// Rows of output per CTA band: as many as fit the exact kernel's shared-memory tile at the
+	// widest format (4 channels), starting from 8.
+	const size_t smem_budget = dev->smem_optin > 0 ? (size_t)dev->smem_optin : 48 * 1024;
+	int band_h = 8, max_rows = 0;
+	std::vector<int> blo, brows;
+	for (;; band_h /= 2) {
+		const int nb = (dh + band_h - 1) / band_h;
+		blo.assign(nb, 0); brows.assign(nb, 0);
+		max_rows = 0;
+		for (int b = 0; b < nb; ++b) {
+			int lo = sh, hi = -1;
+			for (int y = b * band_h; y < dh && y < (b + 1) * band_h; ++y)
+				for (int k = 0; k < p->y.count[y]; ++k) {
+					int r = p->y.eff[p->y.start[y] + k];
+					if (r < lo) lo = r;
+					if (r > hi) hi = r;
+				}
+			blo[b] = lo; brows[b] = hi - lo + 1;
+			if (brows[b] > max_rows) max_rows = brows[b];
+		}
+		if ((size_t)max_rows * 32 * 4 * sizeof(float) <= smem_budget || band_h == 1) break;
+	}
+	if ((size_t)max_rows * 32 * 4 * sizeof(float) > smem_budget) return PICHA_B200_ERR_UNSUPPORTED;
+	const int nb = (dh + band_h - 1) / band_h;
+	if (nb > 65535) return PICHA_B200_ERR_UNSUPPORTED;
+
+	std::vector<uint32_t> blob;
+	auto put_i = [&](const std::vector<int> &v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); return o; };
+	auto put_f = [&](const std::vector<float> &v) {
+		size_t o = blob.size();
+		blob.resize(o + v.size());
+		if (!v.empty()) memcpy(&blob[o], v.data(), v.size() * 4);
+		return o;
+	};
+	size_t o_xfirst = put_i(p->x.first), o_xcount = put_i(p->x.count), o_xstart = put_i(p->x.start);
+	size_t o_ycount = put_i(p->y.count), o_ystart = put_i(p->y.start), o_yeff = put_i(p->y.eff);
+	size_t o_blo = put_i(blo), o_brows = put_i(brows);
+	size_t o_xw = put_f(p->x.w), o_yw = put_f(p->y.w);
+
+	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
+	CU(cudaMemcpy(p->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+	const int *ib = reinterpret_cast<const int *>(p->blob);
+	const float *fb = reinterpret_cast<const float *>(p->blob);
+	p->t.xfirst = ib + o_xfirst; p->t.xcount = ib + o_xcount; p->t.xstart = ib + o_xstart;
+	p->t.ycount = ib + o_ycount; p->t.ystart = ib + o_ystart; p->t.yeff = ib + o_yeff;
+	p->t.band_lo = ib + o_blo; p->t.band_rows = ib + o_brows;
+	p->t.xw = fb + o_xw; p->t.yw = fb + o_yw;
+	p->t.band_h = band_h;
+	p->t.max_band_rows = max_rows;
+
+	dev->plans[key] = p;
+	dev->lru.push_front(key);
+	while (dev->lru.size() > 64) {   // cudaFree of an evicted blob synchronises the device first
+		dev->plans.erase(dev->lru.back());
+		dev->lru.pop_back();
+	}
+	*out = p;
+	return 0;
+}
+
+// ---- validation (what the reference's NAN callers check before reaching the seam) ---------
+
+int check_image(const picha_b200_image *im) {
+	if (!im || !im->data) return PICHA_B200_ERR_INVALID_IMAGE;
+	PixelInfo pi = pixel_info(im->pixel);
+	if (pi.bytes == 0) return PICHA_B200_ERR_INVALID_IMAGE;                    // src/picha.cc:68-69
+	if (im->width < 0 || im->height <= 0) return PICHA_B200_ERR_INVALID_IMAGE;  // src/picha.cc:78 (height != 0)
+	if ((int64_t)im->stride < (int64_t)im->width * pi.bytes) return PICHA_B200_ERR_INVALID_IMAGE;   // lib/image.js:13-14
+	return 0;
+}
+
+int check_resize(const picha_b200_image *s, const picha_b200_image *d, int tag, float width) {
+	int rc = check_image(s);
+	if (rc) return rc;
+	if (s->width <= 0) return PICHA_B200_ERR_INVALID_IMAGE;
+	if (!d || d->width <= 0 || d->height <= 0) return PICHA_B200_ERR_INVALID_DIMENSIONS;   // src/resize.cc:343-346
+	if (tag < 0 || tag >= PICHA_B200_NUM_FILTERS) return PICHA_B200_ERR_INVALID_FILTER;     // src/resize.cc:184-187
+	if (width != width || width <= 0) return PICHA_B200_ERR_INVALID_FILTER_WIDTH;           // src/resize.cc:192-195
+	rc = check_image(d);
+	if (rc) return rc;
+	if (s->pixel != d->pixel) return PICHA_B200_ERR_FORMAT_MISMATCH;                        // src/resize.cc:137
+	return 0;
+}
+
+int check_convert(const picha_b200_image *s, const picha_b200_image *d) {
+	int rc = check_image(s);
+	if (rc) return rc;
+	if (!d) return PICHA_B200_ERR_INVALID_IMAGE;
+	if (pixel_info(d->pixel).bytes == 0) return PICHA_B200_ERR_INVALID_PIXEL;              // src/colorconvert.cc:235-239
+	rc = check_image(d);
+	if (rc) return rc;
+	if (s->width != d->width || s->height != d->height) return PICHA_B200_ERR_SIZE_MISMATCH;   // src/colorconvert.cc:138-139
+	return 0;
+}
+
+bool same_shape(const picha_b200_image &a, const picha_b200_image &b) {
+	return a.width == b.width && a.height == b.height && a.pixel == b.pixel;
+}
+
+// ---- host <-> device staging ---------------------------------------------------------------
+
+bool is_pinned(const void *p) {
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+
+size_t device_pitch(const picha_b200_image &im) {
+	return align_up((size_t)im.width * pixel_info(im.pixel).bytes, 128);
+}
+
+// Host image -> lane->din (pitch `pitch`), asynchronously on the lane's stream.
+int upload(Lane *lane, const picha_b200_image &im, size_t pitch) {
+	const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
+	int rc = lane->din.ensure(pitch * im.height);
+	if (rc) return rc;
+	if (row == 0) return 0;
+	if (is_pinned(im.data)) {
+		CU(cudaMemcpy2DAsync(lane->din.p, pitch, im.data, im.stride, row, im.height, cudaMemcpyHostToDevice, lane->stream));
+		return 0;
+	}
+	rc = lane->hin.ensure(pitch * im.height);
+	if (rc) return rc;
+	const uint8_t *s = static_cast<const uint8_t *>(im.data);
+	for (int y = 0; y < im.height; ++y) memcpy(lane->hin.p + y * pitch, s + (size_t)y * im.stride, row);
+	CU(cudaMemcpyAsync(lane->din.p, lane->hin.p, pitch * im.height, cudaMemcpyHostToDevice, lane->stream));
+	return 0;
+}
+
+// lane->dout -> host image (payload bytes only), asynchronously; staged results are copied out
+// by finish().
+int download(Lane *lane, const picha_b200_image &im, size_t pitch) {
+	const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
+	lane->pending_dst = nullptr;
+	if (row == 0) return 0;
+	if (is_pinned(im.data)) {
+		CU(cudaMemcpy2DAsync(im.data, im.stride, lane->dout.p, pitch, row, im.height, cudaMemcpyDeviceToHost, lane->stream));
+		return 0;
+	}
+	int rc = lane->hout.ensure(pitch * im.height);
+	if (rc) return rc;
+	CU(cudaMemcpyAsync(lane->hout.p, lane->dout.p, pitch * im.height, cudaMemcpyDeviceToHost, lane->stream));
+	lane->pending_dst = &im;
+	lane->pending_pitch = pitch;
+	return 0;
+}
+
+int finish(Lane *lane) {
+	CU(cudaStreamSynchronize(lane->stream));
+	if (lane->pending_dst) {
+		const picha_b200_image &im = *lane->pending_dst;
+		const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
+		uint8_t *d = static_cast<uint8_t *>(im.data);
+		for (int y = 0; y < im.height; ++y) memcpy(d + (size_t)y * im.stride, lane->hout.p + y * lane->pending_pitch, row);
+		lane->pending_dst = nullptr;
+	}
+	return 0;
+}
+
+DevBatch dev_batch(uint8_t *base, int64_t step, size_t pitch, const picha_b200_image &im) {
+	DevBatch b;
+	b.base = base; b.step = step; b.stride = (int)pitch;
+	b.width = im.width; b.height = im.height; b.pixel = im.pixel;
+	return b;
+}
+
+int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag, float width, unsigned flags,
+               cudaStream_t stream) {
+	std::shared_ptr<Plan> plan;
+	int rc = get_plan(dev, tag, width, s.width, s.height, d.width, d.height, &plan);
+	if (rc) return rc;
+	(void)flags;
+	int launches = 0;
+	cudaError_t e = launch_resize_exact(s, d, n, plan->t, stream, &launches);
+	g_launches += launches;
+	if (e == cudaErrorInvalidValue) { cudaGetLastError(); return PICHA_B200_ERR_UNSUPPORTED; }
+	if (e != cudaSuccess) return fail_cuda(e, "resize kernel launch");
+	return 0;
+}
+
+int run_convert(const DevBatch &s, const DevBatch &d, int n, float r, float g, float b, cudaStream_t stream) {
+	int launches = 0;
+	cudaError_t e = launch_color_convert(s, d, n, r, g, b, stream, &launches);
+	g_launches += launches;
+	if (e != cudaSuccess) return fail_cuda(e, "color convert kernel launch");
+	return 0;
+}
+
+struct Op {
+	bool resize;
+	int tag; float width; unsigned flags;   // resize
+	float r, g, b;                          // convert
+};
+
+// One image through one lane: upload, kernel, download (all asynchronous on the lane's stream).
+int submit(Device *dev, Lane *lane, const Op &op, const picha_b200_image &s, const picha_b200_image &d) {
+	const size_t sp = device_pitch(s), dp = device_pitch(d);
+	int rc = upload(lane, s, sp);
+	if (rc) return rc;
+	rc = lane->dout.ensure(dp * d.height);
+	if (rc) return rc;
+	DevBatch sb = dev_batch(lane->din.p, 0, sp, s), db = dev_batch(lane->dout.p, 0, dp, d);
+	rc = op.resize ? run_resize(dev, sb, db, 1, op.tag, op.width, op.flags, lane->stream)
+	               : run_convert(sb, db, 1, op.r, op.g, op.b, lane->stream);
+	if (rc) return rc;
+	return download(lane, d, dp);
+}
+
+// A batch on one device: images round-robin over a few lanes so the copy engines and the SMs
+// overlap (H2D of image i+1 with the kernel of image i and the D2H of image i-1).
+int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *srcs, picha_b200_image *dsts) {
+	Device *dev = get_device(ordinal);
+	if (!dev) { g_last_error = "no such CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
+	CU(cudaSetDevice(ordinal));
+	const int kLanes = n < 4 ? (n < 1 ? 1 : n) : 4;
+	Lane *lanes[4] = {nullptr, nullptr, nullptr, nullptr};
+	bool busy[4] = {false, false, false, false};
+	int rc = 0;
+	for (int l = 0; l < kLanes; ++l) {
+		lanes[l] = dev->acquire();
+		if (!lanes[l]) { rc = PICHA_B200_ERR_CUDA; g_last_error = "cudaStreamCreate failed"; }
+	}
+	for (int i = 0; i < n && !rc; ++i) {
+		const int l = i % kLanes;
+		if (busy[l]) { rc = finish(lanes[l]); busy[l] = false; if (rc) break; }
+		rc = submit(dev, lanes[l], op, srcs[i], dsts[i]);
+		busy[l] = (rc == 0);
+	}
+	for (int l = 0; l < kLanes; ++l) {
+		if (!lanes[l]) continue;
+		if (busy[l]) { int r2 = finish(lanes[l]); if (!rc) rc = r2; }
+		else if (rc) cudaStreamSynchronize(lanes[l]->stream);
+		lanes[l]->pending_dst = nullptr;
+		dev->release(lanes[l]);
+	}
+	return rc;
+}
+
+int run_batch(const Op &op, int n, const picha_b200_image *srcs, picha_b200_image *dsts, int device) {
+	if (n < 0 || (n > 0 && (!srcs || !dsts))) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	for (int i = 0; i < n; ++i) {
+		int rc = op.resize ? check_resize(&srcs[i], &dsts[i], op.tag, op.width) : check_convert(&srcs[i], &dsts[i]);
+		if (rc) return rc;
+	}
+	const int ndev = device_count();
+	if (ndev <= 0) { g_last_error = "no CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
+	if (n == 0) return 0;
+	if (device >= 0) return batch_on_device(device, op, n, srcs, dsts);
+
+	// Shard contiguous blocks of the batch across every GPU; independent images, no collective.
+	const int shards = n < ndev ? n : ndev;
+	std::vector<int> rcs(shards, 0);
+	std::vector<std::string> errs(shards);
+	std::vector<std::thread> threads;
+	for (int s = 0; s < shards; ++s) {
+		const int lo = (int)((int64_t)n * s / shards), hi = (int)((int64_t)n * (s + 1) / shards);
+		threads.emplace_back([&, s, lo, hi]() {
+			rcs[s] = batch_on_device(s, op, hi - lo, srcs + lo, dsts + lo);
+			if (rcs[s]) errs[s] = g_last_error;
+		});
+	}
+	for (auto &t : threads) t.join();
+	for (int s = 0; s < shards; ++s)
+		if (rcs[s]) { g_last_error = errs[s]; return rcs[s]; }
+	return 0;
+}
+
+int current_device_checked(Device **out) {
+	if (device_count() <= 0) { g_last_error = "no CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
+	int ord = 0;
+	CU(cudaGetDevice(&ord));
+	*out = get_device(ord);
+	return *out ? 0 : PICHA_B200_ERR_NO_DEVICE;
+}
+
+}  // namespace
+
+int max_dynamic_smem() {
+	int dev = 0, v = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return 48 * 1024;
+	if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) return 48 * 1024;
+	return v;
+}
+
+}  // namespace picha_b200
+
+using namespace picha_b200;
+
+extern "C" {
+
+int picha_b200_version(void) { return PICHA_B200_VERSION; }
+
+int picha_b200_device_count(void) { return device_count(); }
+
+int picha_b200_init(int device) {
+	const int n = device_count();
+	if (n <= 0) { g_last_error = "no CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
+	if (device >= n) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	for (int d = (device < 0 ? 0 : device); d < (device < 0 ? n : device + 1); ++d) {
+		Device *dev = get_device(d);
+		CU(cudaSetDevice(d));
+		CU(cudaFree(0));
+		Lane *l = dev->acquire();
+		if (!l) return PICHA_B200_ERR_CUDA;
+		dev->release(l);
+	}
+	if (device >= 0) g_default_device.store(device);
+	return 0;
+}
+
+void picha_b200_shutdown(void) {
+	std::lock_guard<std::mutex> g(g_devices_mu);
+	for (Device *d : g_devices) {
+		if (!d) continue;
+		cudaSetDevice(d->id);
+		cudaDeviceSynchronize();
+		for (Lane *l : d->all) {
+			l->hin.release(); l->hout.release(); l->din.release(); l->dout.release();
+			if (l->stream) cudaStreamDestroy(l->stream);
+			delete l;
+		}
+		d->plans.clear();
+		delete d;
+	}
+	g_devices.assign(g_devices.size(), nullptr);
+}
+
+const char *picha_b200_strerror(int status) {
+	switch (status) {
+		case PICHA_B200_OK: return "ok";
+		case PICHA_B200_ERR_INVALID_IMAGE: return "invalid image";
+		case PICHA_B200_ERR_INVALID_DIMENSIONS: return "invalid dimensions";
+		case PICHA_B200_ERR_INVALID_FILTER: return "invalid filter mode";
+		case PICHA_B200_ERR_INVALID_FILTER_WIDTH: return "invalid filter width";
+		case PICHA_B200_ERR_INVALID_PIXEL: return "expected pixel mode";
+		case PICHA_B200_ERR_FORMAT_MISMATCH: return "source and destination pixel formats differ";
+		case PICHA_B200_ERR_SIZE_MISMATCH: return "source and destination dimensions differ";
+		case PICHA_B200_ERR_NO_DEVICE: return "no CUDA device (picha_b200 has no CPU fallback)";
+		case PICHA_B200_ERR_CUDA: return "CUDA error";
+		case PICHA_B200_ERR_NOMEM: return "out of memory";
+		case PICHA_B200_ERR_UNSUPPORTED: return "unsupported shape";
+		case PICHA_B200_ERR_INVALID_ARGUMENT: return "invalid argument";
+	}
+	return "unknown status";
+}
+
+const char *picha_b200_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t picha_b200_launch_count(void) { return g_launches.load(); }
+
+int picha_b200_pixel_bytes(int pixel) { return pixel_info(pixel).bytes; }
+int picha_b200_pixel_channels(int pixel) { return pixel_info(pixel).channels; }
+int picha_b200_row_stride(int width, int pixel) { return (pixel_info(pixel).bytes * width + 3) & ~3; }
+
+int picha_b200_resolve_resize_options(int has_filter, int filter_tag, int has_filter_scale, double filter_scale,
+                                      int *tag_out, float *width_out) {
+	int tag = PICHA_B200_CUBIC;
+	float width = 0.70f;                                     // ResizeOptions(), src/resize.cc:174
+	if (has_filter) {
+		width = 1.0f;                                        // :182
+		if (filter_tag < 0 || filter_tag >= PICHA_B200_NUM_FILTERS) return PICHA_B200_ERR_INVALID_FILTER;
+		tag = filter_tag;
+	}
+	if (has_filter_scale) {
+		width = (float)filter_scale;                         // :191
+		if (width != width || width <= 0) return PICHA_B200_ERR_INVALID_FILTER_WIDTH;
+	}
+	if (tag_out) *tag_out = tag;
+	if (width_out) *width_out = width;
+	return 0;
+}
+
+void picha_b200_resolve_color_settings(double red, double green, double blue, float out[3]) {
+	float r = 0.299f, g = 0.587f, b = float(0.114);          // src/colorconvert.h:12
+	if (red == red) r = (float)red;                          // src/colorconvert.cc:11
+	if (green == green) g = (float)green;
+	if (blue == blue) b = (float)blue;
+	const float n = 1.0f / (r + g + b);                      // :18
+	out[0] = r * n; out[1] = g * n; out[2] = b * n;
+}
+
+int picha_b200_resize_ex(const picha_b200_image *src, picha_b200_image *dst, int filter_tag, float filter_width,
+                         unsigned flags) {
+	Op op{};
+	op.resize = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags;
+	if (!src || !dst) return PICHA_B200_ERR_INVALID_IMAGE;
+	return run_batch(op, 1, src, dst, default_ordinal());
+}
+
+int picha_b200_resize(const picha_b200_image *src, picha_b200_image *dst, int filter_tag, float filter_width) {
+	return picha_b200_resize_ex(src, dst, filter_tag, filter_width, 0);
+}
+
+int picha_b200_color_convert(const picha_b200_image *src, picha_b200_image *dst, float r, float g, float b) {
+	Op op{};
+	op.resize = false; op.r = r; op.g = g; op.b = b;
+	if (!src || !dst) return PICHA_B200_ERR_INVALID_IMAGE;
+	return run_batch(op, 1, src, dst, default_ordinal());
+}
+
+int picha_b200_resize_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, int filter_tag,
+                            float filter_width, unsigned flags, int device) {
+	Op op{};
+	op.resize = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags;
+	return run_batch(op, n, srcs, dsts, device);
+}
+
+int picha_b200_color_convert_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, float r, float g,
+                                   float b, int device) {
+	Op op{};
+	op.resize = false; op.r = r; op.g = g; op.b = b;
+	return run_batch(op, n, srcs, dsts, device);
+}
+
+void *picha_b200_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (device_count() <= 0) return nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+void picha_b200_host_free(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+int picha_b200_resize_device(int n, const picha_b200_image *src0, int64_t src_step, const picha_b200_image *dst0,
+                             int64_t dst_step, int filter_tag, float filter_width, unsigned flags, void *stream) {
+	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	int rc = check_resize(src0, dst0, filter_tag, filter_width);
+	if (rc) return rc;
+	Device *dev = nullptr;
+	rc = current_device_checked(&dev);
+	if (rc) return rc;
+	if (n == 0) return 0;
+	DevBatch s = dev_batch(static_cast<uint8_t *>(src0->data), src_step, src0->stride, *src0);
+	DevBatch d = dev_batch(static_cast<uint8_t *>(dst0->data), dst_step, dst0->stride, *dst0);
+	return run_resize(dev, s, d, n, filter_tag, filter_width, flags, static_cast<cudaStream_t>(stream));
+}
+
+int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t src_step, const picha_b200_image *dst0,
+                                    int64_t dst_step, float r, float g, float b, void *stream) {
+	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	int rc = check_convert(src0, dst0);
+	if (rc) return rc;
+	Device *dev = nullptr;
+	rc = current_device_checked(&dev);
+	if (rc) return rc;
+	if (n == 0) return 0;
+	DevBatch s = dev_batch(static_cast<uint8_t *>(src0->data), src_step, src0->stride, *src0);
+	DevBatch d = dev_batch(static_cast<uint8_t *>(dst0->data), dst_step, dst0->stride, *dst0);
+	return run_convert(s, d, n, r, g, b, static_cast<cudaStream_t>(stream));
+}
+
+int picha_b200_synthetic_fill_device(int n, const picha_b200_image *img0, int64_t step, uint64_t seed,
+                                     uint64_t first_image, void *stream) {
+	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	int rc = check_image(img0);
+	if (rc) return rc;
+	Device *dev = nullptr;
+	rc = current_device_checked(&dev);
+	if (rc) return rc;
+	if (n == 0 || img0->width == 0) return 0;
+	DevBatch b = dev_batch(static_cast<uint8_t *>(img0->data), step, img0->stride, *img0);
+	int launches = 0;
+	cudaError_t e = launch_synthetic_fill(b, n, seed, first_image, static_cast<cudaStream_t>(stream), &launches);
+	g_launches += launches;
+	if (e != cudaSuccess) return fail_cuda(e, "synthetic fill launch");
+	return 0;
+}
+
+int picha_b200_contribs(int filter_tag, float filter_width, int srcsize, int dstsize, int *left, int *count,
+                        int *offset, float *weights, int *eff_row, int cap) {
+	if (filter_tag < 0 || filter_tag >= PICHA_B200_NUM_FILTERS) return PICHA_B200_ERR_INVALID_FILTER;
+	if (filter_width != filter_width || filter_width <= 0) return PICHA_B200_ERR_INVALID_FILTER_WIDTH;
+	if (srcsize <= 0 || dstsize <= 0) return PICHA_B200_ERR_INVALID_DIMENSIONS;
+	AxisTable t;
+	build_axis(filter_tag, filter_width, srcsize, dstsize, t);
+	for (int i = 0; i < dstsize; ++i) {
+		if (left) left[i] = t.first[i];
+		if (count) count[i] = t.count[i];
+		if (offset) offset[i] = t.start[i];
+	}
+	const int n = (int)t.w.size();
+	for (int i = 0; i < n && i < cap; ++i) {
+		if (weights) weights[i] = t.w[i];
+		if (eff_row) eff_row[i] = t.eff[i];
+	}
+	return n;
+}
+
+}  // extern "C"

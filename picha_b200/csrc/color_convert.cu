@@ -1,0 +1,310 @@
+// Pixel-format conversion kernels (reference: ColorConverter<Src,Dst>::op, src/colorconvert.cc:136-152,
+// with the thirteen ChannelConvertOp specialisations of :24-134).
+//
+// The reference round-trips every channel through float (unpack -> op -> pack).  For everything
+// except luma that round trip is an integer identity, verified for every u8/u16 value against the
+// reference's own output (tests/test_oracle.py::test_depth_identities):
+//     same depth: v            u8 -> u16: v * 257            u16 -> u8: (v * 255 + 32767) / 65535
+//     constants:  1.0f -> max  0.0f -> 0
+// Luma ((s0*r + s1*g) + s2*b, :90) is float and must not be contracted into FMAs, or 12 pixels
+// of a 1080p frame come out one LSB off; pixel.cuh's *_rn intrinsics guarantee that.
+//
+// Two kernels:
+//   convert_rows_kernel  -- the bandwidth path: a warp converts 128 pixels per step; global
+//       traffic is 32-bit-per-lane fully coalesced (every 128-byte line is touched by exactly
+//       one request) and the word -> pixel regrouping goes through a warp-private shared-memory
+//       tile, so 3- and 6-byte pixels cost the same as the power-of-two ones.
+//       Needs 4-byte aligned row starts on both sides.
+//   convert_pixels_kernel -- any alignment / stride / width (subView inputs, row tails).
+#include "kernels.h"
+#include "pixel.cuh"
+
+namespace picha_b200 {
+
+namespace {
+
+template <bool SDEEP, bool DDEEP> __device__ __forceinline__ unsigned depth_convert(unsigned v) {
+	if (SDEEP == DDEEP) return v;
+	if (DDEEP) return v * 257u;
+	return (v * 255u + 32767u) / 65535u;
+}
+
+// One pixel, on integer channel values. SC/DC: channel counts. src/colorconvert.cc:24-134.
+template <int SC, bool SDEEP, int DC, bool DDEEP>
+__device__ __forceinline__ void convert_pixel(const unsigned *in, unsigned *out, float rf, float gf, float bf) {
+	constexpr unsigned ONE = DDEEP ? 65535u : 255u;
+	if constexpr (SC >= 3 && DC <= 2) {          // 3->1, 3->2, 4->1, 4->2: luma (alpha ignored or passed through)
+		float r = unpack_value<SDEEP>(in[0]);
+		float g = unpack_value<SDEEP>(in[1]);
+		float b = unpack_value<SDEEP>(in[2]);
+		float l = __fadd_rn(__fadd_rn(__fmul_rn(r, rf), __fmul_rn(g, gf)), __fmul_rn(b, bf));
+		out[0] = pack_value<DDEEP>(l);
+		if constexpr (DC == 2) out[1] = (SC == 4) ? depth_convert<SDEEP, DDEEP>(in[3]) : ONE;
+	} else {
+	unsigned v[4];
+#pragma unroll
+	for (int c = 0; c < SC; ++c) v[c] = depth_convert<SDEEP, DDEEP>(in[c]);
+	if constexpr (SC == DC) {
+#pragma unroll
+		for (int c = 0; c < DC; ++c) out[c] = v[c];
+	} else if constexpr (SC == 1) {              // 1->2 (g,1)  1->3 (g,g,g)  1->4 (g,g,g,1)
+		out[0] = v[0];
+		if constexpr (DC == 2) out[1] = ONE;
+		if constexpr (DC >= 3) { out[1] = v[0]; out[2] = v[0]; }
+		if constexpr (DC == 4) out[3] = ONE;
+	} else if constexpr (SC == 2) {              // 2->1 g   2->3 (g,a,0)   2->4 (g,g,g,a)
+		out[0] = v[0];
+		if constexpr (DC == 3) { out[1] = v[1]; out[2] = 0u; }
+		if constexpr (DC == 4) { out[1] = v[0]; out[2] = v[0]; out[3] = v[1]; }
+	} else if constexpr (SC == 3) {              // 3->4 (r,g,b,1)
+		out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; out[3] = ONE;
+	} else {                           // 4->3 (r,g,b)
+		out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+	}
+	}
+}
+
+constexpr int kWarps = 8;
+constexpr int kGroup = 128;   // pixels per warp step: 4 per lane
+
+// Channel i of a little-endian word array.
+template <bool DEEP> __device__ __forceinline__ unsigned word_get(const unsigned *w, int i) {
+	if (DEEP) return (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+	return (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+}
+template <bool DEEP> __device__ __forceinline__ void word_put(unsigned *w, int i, unsigned v) {
+	if (DEEP) w[i >> 1] |= v << (16 * (i & 1));
+	else w[i >> 2] |= v << (8 * (i & 3));
+}
+
+// A lane's N consecutive words of a warp tile, with the widest shared-memory access N allows
+// (scalar accesses at an even word stride would be 2- to 8-way bank conflicted).
+template <int N> __device__ __forceinline__ void lane_words_load(unsigned *r, const unsigned *tile, int lane) {
+	if constexpr (N % 4 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 4; ++j) {
+			uint4 v = reinterpret_cast<const uint4 *>(tile)[lane * (N / 4) + j];
+			r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+		}
+	} else if constexpr (N % 2 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 2; ++j) {
+			uint2 v = reinterpret_cast<const uint2 *>(tile)[lane * (N / 2) + j];
+			r[2 * j] = v.x; r[2 * j + 1] = v.y;
+		}
+	} else {
+#pragma unroll
+		for (int j = 0; j < N; ++j) r[j] = tile[lane * N + j];
+	}
+}
+template <int N> __device__ __forceinline__ void lane_words_store(unsigned *tile, const unsigned *r, int lane) {
+	if constexpr (N % 4 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 4; ++j)
+			reinterpret_cast<uint4 *>(tile)[lane * (N / 4) + j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+	} else if constexpr (N % 2 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 2; ++j)
+			reinterpret_cast<uint2 *>(tile)[lane * (N / 2) + j] = make_uint2(r[2 * j], r[2 * j + 1]);
+	} else {
+#pragma unroll
+		for (int j = 0; j < N; ++j) tile[lane * N + j] = r[j];
+	}
+}
+
+template <int SC, bool SDEEP, int DC, bool DDEEP>
+__device__ __forceinline__ void convert_one_unaligned(const uint8_t *s, uint8_t *d, float rf, float gf, float bf) {
+	unsigned in[4], out[4];
+#pragma unroll
+	for (int c = 0; c < SC; ++c) in[c] = load_channel<SDEEP>(s + c * Depth<SDEEP>::bytes);
+	convert_pixel<SC, SDEEP, DC, DDEEP>(in, out, rf, gf, bf);
+#pragma unroll
+	for (int c = 0; c < DC; ++c) store_channel<DDEEP>(d + c * Depth<DDEEP>::bytes, out[c]);
+}
+
+template <int SC, bool SDEEP, int DC, bool DDEEP>
+__global__ void __launch_bounds__(kWarps * 32)
+convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, long long total_groups, float rf, float gf, float bf) {
+	constexpr int SW = SC * Depth<SDEEP>::bytes;   // source words per lane per step (= bytes per pixel)
+	constexpr int DW = DC * Depth<DDEEP>::bytes;
+	__shared__ __align__(16) unsigned tile_in[kWarps][SW * 32];
+	__shared__ __align__(16) unsigned tile_out[kWarps][DW * 32];
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned *tin = tile_in[warp], *tout = tile_out[warp];
+	const long long groups_per_image = (long long)groups_per_row * src.height;
+
+	for (long long g = (long long)blockIdx.x * kWarps + warp; g < total_groups; g += (long long)gridDim.x * kWarps) {
+		const long long img = g / groups_per_image;
+		const int rem = (int)(g - img * groups_per_image);
+		const int y = rem / groups_per_row, gx = rem - y * groups_per_row;
+		const int px0 = gx * kGroup;
+		const uint8_t *srow = src.base + img * src.step + (long long)y * src.stride + (long long)px0 * SW;
+		uint8_t *drow = dst.base + img * dst.step + (long long)y * dst.stride + (long long)px0 * DW;
+		const int npx = min(kGroup, src.width - px0);
+
+		if (npx == kGroup) {
+			const unsigned *s32 = reinterpret_cast<const unsigned *>(srow);
+			unsigned win[SW];
+#pragma unroll
+			for (int j = 0; j < SW; ++j) win[j] = __ldg(s32 + j * 32 + lane);
+			__syncwarp();   // previous step's readers are done with the tiles
+#pragma unroll
+			for (int j = 0; j < SW; ++j) tin[j * 32 + lane] = win[j];
+			__syncwarp();
+			unsigned mine[SW];
+			lane_words_load<SW>(mine, tin, lane);
+
+			unsigned packed[DW];
+#pragma unroll
+			for (int j = 0; j < DW; ++j) packed[j] = 0u;
+#pragma unroll
+			for (int p = 0; p < 4; ++p) {
+				unsigned in[4], out[4];
+#pragma unroll
+				for (int c = 0; c < SC; ++c) in[c] = word_get<SDEEP>(mine, p * SC + c);
+				convert_pixel<SC, SDEEP, DC, DDEEP>(in, out, rf, gf, bf);
+#pragma unroll
+				for (int c = 0; c < DC; ++c) word_put<DDEEP>(packed, p * DC + c, out[c]);
+			}
+			lane_words_store<DW>(tout, packed, lane);
+			__syncwarp();
+			unsigned *d32 = reinterpret_cast<unsigned *>(drow);
+#pragma unroll
+			for (int j = 0; j < DW; ++j) d32[j * 32 + lane] = tout[j * 32 + lane];
+		} else {
+			// row tail: fewer than 128 pixels left; only payload bytes may be written
+			for (int p = lane; p < npx; p += 32)
+				convert_one_unaligned<SC, SDEEP, DC, DDEEP>(srow + p * SW, drow + p * DW, rf, gf, bf);
+		}
+	}
+}
+
+template <int SC, bool SDEEP, int DC, bool DDEEP>
+__global__ void __launch_bounds__(256)
+convert_pixels_kernel(DevBatch src, DevBatch dst, float rf, float gf, float bf) {
+	constexpr int SB = SC * Depth<SDEEP>::bytes, DB = DC * Depth<DDEEP>::bytes;
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	if (x >= src.width) return;
+	for (int y = blockIdx.y; y < src.height; y += gridDim.y) {
+		const uint8_t *s = src.base + (long long)blockIdx.z * src.step + (long long)y * src.stride + (long long)x * SB;
+		uint8_t *d = dst.base + (long long)blockIdx.z * dst.step + (long long)y * dst.stride + (long long)x * DB;
+		convert_one_unaligned<SC, SDEEP, DC, DDEEP>(s, d, rf, gf, bf);
+	}
+}
+
+// Same format: NativeImage::copy, src/picha.cc:27-34 -- payload bytes of each row.
+__global__ void __launch_bounds__(256)
+copy_rows_kernel(DevBatch src, DevBatch dst, int row_bytes, int vec_ok) {
+	const uint8_t *s = src.base + (long long)blockIdx.z * src.step + (long long)blockIdx.y * src.stride;
+	uint8_t *d = dst.base + (long long)blockIdx.z * dst.step + (long long)blockIdx.y * dst.stride;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+	int done = 0;
+	if (vec_ok) {
+		const int nvec = row_bytes >> 4;
+		const uint4 *s4 = reinterpret_cast<const uint4 *>(s);
+		uint4 *d4 = reinterpret_cast<uint4 *>(d);
+		for (int i = tid; i < nvec; i += nth) d4[i] = __ldg(s4 + i);
+		done = nvec << 4;
+	}
+	for (int i = done + tid; i < row_bytes; i += nth) d[i] = s[i];
+}
+
+bool aligned4(const DevBatch &b) {
+	return (reinterpret_cast<uintptr_t>(b.base) & 3) == 0 && (b.stride & 3) == 0 && (b.step & 3) == 0;
+}
+bool aligned16(const DevBatch &b) {
+	return (reinterpret_cast<uintptr_t>(b.base) & 15) == 0 && (b.stride & 15) == 0 && (b.step & 15) == 0;
+}
+
+int sm_count() {
+	static int n = 0;
+	if (!n) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+	}
+	return n;
+}
+
+template <int SC, bool SDEEP, int DC, bool DDEEP>
+cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float rf, float gf, float bf,
+                        cudaStream_t stream, int *launches) {
+	if (aligned4(src) && aligned4(dst)) {
+		const int gpr = (src.width + kGroup - 1) / kGroup;
+		const long long total = (long long)gpr * src.height * n;
+		// persistent-style grid: a multiple of the SM count, capped by the work available
+		long long want = (total + kWarps - 1) / kWarps;
+		long long cap = (long long)sm_count() * 16;
+		int grid = (int)(want < cap ? want : cap);
+		if (grid < 1) grid = 1;
+		convert_rows_kernel<SC, SDEEP, DC, DDEEP><<<grid, kWarps * 32, 0, stream>>>(src, dst, gpr, total, rf, gf, bf);
+		*launches += 1;
+		return cudaGetLastError();
+	}
+	for (int z0 = 0; z0 < n; z0 += 65535) {
+		const int nz = n - z0 < 65535 ? n - z0 : 65535;
+		DevBatch s = src, d = dst;
+		s.base += (long long)z0 * src.step;
+		d.base += (long long)z0 * dst.step;
+		dim3 grid((src.width + 255) / 256, src.height < 65535 ? src.height : 65535, nz);
+		convert_pixels_kernel<SC, SDEEP, DC, DDEEP><<<grid, 256, 0, stream>>>(s, d, rf, gf, bf);
+		*launches += 1;
+	}
+	return cudaGetLastError();
+}
+
+template <int SC, bool SDEEP>
+cudaError_t launch_src(const DevBatch &src, const DevBatch &dst, int n, float rf, float gf, float bf,
+                       cudaStream_t stream, int *launches) {
+	switch (dst.pixel) {
+		case 0: return launch_pair<SC, SDEEP, 3, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 1: return launch_pair<SC, SDEEP, 4, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 2: return launch_pair<SC, SDEEP, 1, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 3: return launch_pair<SC, SDEEP, 2, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 4: return launch_pair<SC, SDEEP, 1, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 5: return launch_pair<SC, SDEEP, 2, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 6: return launch_pair<SC, SDEEP, 3, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 7: return launch_pair<SC, SDEEP, 4, true>(src, dst, n, rf, gf, bf, stream, launches);
+	}
+	return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+cudaError_t launch_color_convert(const DevBatch &src, const DevBatch &dst, int n, float rf, float gf, float bf,
+                                 cudaStream_t stream, int *launches) {
+	if (n <= 0 || src.width <= 0 || src.height <= 0) return cudaSuccess;
+	if (src.pixel == dst.pixel) {
+		static const int bytes[8] = {3, 4, 1, 2, 2, 4, 6, 8};
+		const int row_bytes = src.width * bytes[src.pixel];
+		const int vec_ok = aligned16(src) && aligned16(dst);
+		for (int z0 = 0; z0 < n; z0 += 65535)
+			for (int y0 = 0; y0 < src.height; y0 += 65535) {
+				DevBatch s = src, d = dst;
+				s.base += (long long)z0 * src.step + (long long)y0 * src.stride;
+				d.base += (long long)z0 * dst.step + (long long)y0 * dst.stride;
+				const int nz = n - z0 < 65535 ? n - z0 : 65535;
+				const int ny = src.height - y0 < 65535 ? src.height - y0 : 65535;
+				int gx = (row_bytes / 16 + 255) / 256;
+				if (gx < 1) gx = 1;
+				if (gx > 8) gx = 8;
+				copy_rows_kernel<<<dim3(gx, ny, nz), 256, 0, stream>>>(s, d, row_bytes, vec_ok);
+				*launches += 1;
+			}
+		return cudaGetLastError();
+	}
+	switch (src.pixel) {
+		case 0: return launch_src<3, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 1: return launch_src<4, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 2: return launch_src<1, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 3: return launch_src<2, false>(src, dst, n, rf, gf, bf, stream, launches);
+		case 4: return launch_src<1, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 5: return launch_src<2, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 6: return launch_src<3, true>(src, dst, n, rf, gf, bf, stream, launches);
+		case 7: return launch_src<4, true>(src, dst, n, rf, gf, bf, stream, launches);
+	}
+	return cudaErrorInvalidValue;
+}
+
+}  // namespace picha_b200

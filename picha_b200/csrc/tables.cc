@@ -1,0 +1,118 @@
+// See tables.h.  Compiled with -ffp-contract=off: the reference build has no FMA.
+#include "tables.h"
+
+#include <cmath>
+
+namespace picha_b200 {
+namespace {
+
+// Piecewise cubic with the (B, C) parametrisation; src/resize.cc:210-231.
+struct BCSpline {
+	float p0, p2, p3, q0, q1, q2, q3;
+	BCSpline(float B, float C) {
+		p3 = (12 - 9 * B - 6 * C) / 6;
+		p2 = (-18 + 12 * B + 6 * C) / 6;
+		p0 = (6 - 2 * B) / 6;
+		q3 = (-B - 6 * C) / 6;
+		q2 = (6 * B + 30 * C) / 6;
+		q1 = (-12 * B - 48 * C) / 6;
+		q0 = (8 * B + 24 * C) / 6;
+	}
+	float at(float o) const {
+		float x = std::fabs(o);
+		if (x < 1) return p0 + (x * x * (p2 + x * p3));
+		return q0 + (x * (q1 + x * (q2 + x * q3)));
+	}
+};
+
+class Kernel1D {
+public:
+	Kernel1D(int tag, float width) : tag_(tag), width_(width), catmul_(0.0f, 0.5f), mitchel_(0.333f, 0.333f) {}
+
+	// ScaledFilter::support, src/resize.cc:266
+	float support() const {
+		float base = 2.0f;                       // cubic, lanczos<2>, catmulrom, mitchel
+		if (tag_ == 5) base = 1.0f;              // triangle, :201
+		else if (tag_ == 4) base = 0.5f;         // box, :206
+		return width_ * base;
+	}
+	// ScaledFilter::operator(), src/resize.cc:267
+	float operator()(float f) const { return base(f / width_) / width_; }
+
+private:
+	float base(float o) const {
+		switch (tag_) {
+			case 1: {                            // lanczos A=2, :249-252
+				float x = o * float(M_PI), x2 = x * x;
+				return x2 == 0 ? 1.0f : 2u * std::sin(x) * std::sin(x / 2u) / x2;
+			}
+			case 2: return catmul_.at(o);
+			case 3: return mitchel_.at(o);
+			case 4: return 1.0f;                 // box has no cut-off, :207
+			case 5: return 1.0f - std::fabs(o);  // :202
+			default: {                           // cubic, :259
+				float a = std::fabs(o);
+				return 1.0f - a * a * (0.75f - 0.25f * a);
+			}
+		}
+	}
+	int tag_;
+	float width_;
+	BCSpline catmul_, mitchel_;
+};
+
+}  // namespace
+
+void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTable &t) {
+	const Kernel1D k(filter_tag, width);
+	t = AxisTable();
+	t.src_size = src_size;
+	t.dst_size = dst_size;
+	t.scale = src_size / float(dst_size);                                   // resize.cc:72-73
+	const float fscale = std::fmax(std::fmax(t.scale, 1.0f), 1.0f / k.support());
+	t.fsupport = k.support() * fscale;
+	t.ring = int(std::ceil(2 * t.fsupport));
+	const float inv = 1.0f / fscale;
+
+	t.first.resize(dst_size);
+	t.count.resize(dst_size);
+	t.start.resize(dst_size);
+	t.need.resize(dst_size);
+	t.w.reserve(size_t(t.ring + 2) * dst_size);
+
+	float centre = 0.5f * t.scale;
+	for (int i = 0; i < dst_size; ++i, centre += t.scale) {                 // float accumulation on purpose
+		int lo = int(std::fmax(0.0f, std::ceil(centre - t.fsupport)));
+		int hi = int(std::fmin(float(src_size - 1), std::floor(centre + t.fsupport)));
+		while (lo < hi && k((centre - lo) * inv) == 0) ++lo;                 // exact-zero end taps are dropped
+		while (hi > lo && k((centre - hi) * inv) == 0) --hi;
+		t.first[i] = lo;
+		t.count[i] = hi - lo + 1;
+		t.start[i] = int(t.w.size());
+		if (t.count[i] > t.max_taps) t.max_taps = t.count[i];
+		float sum = 0;
+		for (int j = lo; j <= hi; ++j) {
+			float wgt = k((centre - float(j)) * inv);
+			t.w.push_back(wgt);
+			sum += wgt;
+		}
+		const float norm = 1.0f / sum;   // the reference asserts sum > 0 in debug builds and divides regardless in release
+		for (size_t j = t.start[i]; j < t.w.size(); ++j) t.w[j] *= norm;
+
+		int need = int(centre + t.fsupport);                                // resize.cc:104
+		t.need[i] = need < src_size - 1 ? need : src_size - 1;
+	}
+
+	// Ring model: when output row i is produced every source row <= need[i] has been written
+	// to slot row % M, so slot c % M holds the newest such row congruent to c.
+	t.eff.resize(t.w.size());
+	const int M = t.ring > 0 ? t.ring : 1;
+	for (int i = 0; i < dst_size; ++i)
+		for (int q = 0; q < t.count[i]; ++q) {
+			int c = t.first[i] + q;
+			int lag = t.need[i] - c;
+			t.eff[t.start[i] + q] = lag >= 0 ? c + M * (lag / M) : c;
+		}
+}
+
+}  // namespace picha_b200

@@ -1,0 +1,390 @@
+"""Parity of the CUDA path with the oracle, through the C-ABI (run with -m gpu on a B200).
+
+colorConvert: bit-exact.  resize: bit-exact in EXACT mode; the default (fast) mode must be within
++-1 LSB per channel and mean |diff| <= 0.05 (uint16 steps for the r16* formats) -- the tolerance
+BASELINE.json's north_star states.
+"""
+import ctypes
+import itertools
+import threading
+
+import numpy as np
+import pytest
+
+import oracle as O
+from picha_b200 import _native as N
+from picha_b200.image import Image, PIXEL_NAMES
+from picha_b200.synthetic import fill_host
+
+pytestmark = pytest.mark.gpu
+
+MAX_LSB = 1
+MEAN_LSB = 0.05
+
+
+def rand_image(rng, w, h, pixel, pad=0, offset=0):
+    bpp = O.PIXEL_BYTES[O.PIXELS.index(pixel)]
+    stride = ((w * bpp + 3) & ~3) + pad
+    raw = rng.integers(0, 256, stride * h + offset, dtype=np.uint8)
+    return Image({"width": w, "height": h, "pixel": pixel, "stride": stride, "data": raw[offset:]})
+
+
+def chan(img):
+    r = np.ascontiguousarray(img.rows())
+    return r.view(np.uint16) if PIXEL_NAMES.index(img.pixel if img.pixel != "r16b16" else "r16g16") >= 4 else r
+
+
+def oracle_resize(img, dw, dh, filt, fw):
+    d, ds = O.resize(np.ascontiguousarray(img.data), img.stride, img.width, img.height, img.pixel, dw, dh, filt, fw)
+    return Image({"width": dw, "height": dh, "pixel": img.pixel, "stride": ds, "data": d})
+
+
+def assert_resize_close(got, want, exact, ctx):
+    a, b = chan(got).astype(np.int64), chan(want).astype(np.int64)
+    d = np.abs(a - b)
+    if exact:
+        assert d.max() == 0, (ctx, "exact mode differs", int(d.max()), float(d.mean()))
+    else:
+        assert d.max() <= MAX_LSB and d.mean() <= MEAN_LSB, (ctx, int(d.max()), float(d.mean()))
+
+
+# ---- the reference's own tests, transliterated -------------------------------------------------
+
+def test_resize_fixture_sync_and_async(gpu, fixtures):
+    """test/resize.js:17-30."""
+    P = gpu
+    rows = fixtures["test2_jpg_rgb"]
+    h, w, _ = rows.shape
+    image = Image({"width": w, "height": h, "pixel": "rgb"})
+    for y in range(h):
+        image.row(y)[:] = rows[y].reshape(-1)
+    small = Image({"width": 32, "height": 24, "pixel": "rgb"})
+    for y in range(24):
+        small.row(y)[:] = fixtures["test2_png_rgb"][y].reshape(-1)
+    opts = {"width": 32, "height": 24}
+    box = {}
+    done = threading.Event()
+
+    def cb(err, o):
+        box["err"], box["img"] = err, o
+        done.set()
+
+    P.resize(image, opts, cb)
+    assert done.wait(60) and box["err"] is None
+    async_small = box["img"]
+    assert async_small.avgChannelDiff(small) < 2
+    sync_small = P.resizeSync(image, opts)
+    assert sync_small.avgChannelDiff(small) < 2
+    assert sync_small.equalPixels(async_small)
+    # stronger than the reference's own bound: north_star tolerance, and bit-exact in exact mode
+    assert_resize_close(sync_small, small, False, "fixture")
+    assert P.resizeSync(image, dict(opts, exact=True)).equalPixels(small)
+
+
+def test_colour_fixture(gpu, fixtures):
+    """test/color_convert.js:16-39."""
+    P = gpu
+    rgba = Image({"width": 50, "height": 50, "pixel": "rgba", "data": fixtures["test_png_rgba"].reshape(-1).copy()})
+    grey = Image({"width": 50, "height": 50, "pixel": "greya", "data": fixtures["greytest_png_greya"].reshape(-1).copy()})
+    to_grey = P.colorConvertSync(rgba, {"pixel": "greya"})
+    assert to_grey.pixel == "greya" and to_grey.width == 50 and to_grey.height == 50
+    assert to_grey.equalPixels(grey)
+    box = {}
+    done = threading.Event()
+
+    def cb2(err, rimg):
+        box["err"], box["img"] = err, rimg
+        done.set()
+
+    def cb1(err, img):
+        assert err is None
+        P.colorConvert(img, {"pixel": grey.pixel}, cb2)
+
+    P.colorConvert(grey, {"pixel": "rgba"}, cb1)
+    assert done.wait(60) and box["err"] is None
+    assert grey.equalPixels(box["img"])
+
+
+def test_committed_reference_vectors(gpu, ref_vectors):
+    """Outputs of the reference's own C++ (tests/golden/ref_vectors.npz) straight against the GPU."""
+    P = gpu
+    weights = [None, (0.2, 0.5, 0.3), (1, 1, 1)]
+    for row in ref_vectors["meta"]:
+        kind, k = int(row[0]), int(row[1])
+        if kind == 0:
+            p, f, sw, sh, dw, dh = (int(v) for v in row[2:8])
+            fw, ss = float(row[8]), int(row[9])
+            img = Image({"width": sw, "height": sh, "pixel": PIXEL_NAMES[p], "stride": ss, "data": ref_vectors[f"rs{k}_src"].copy()})
+            want = ref_vectors[f"rs{k}_dst"]
+            for exact in (True, False):
+                got = P.resizeSync(img, {"width": dw, "height": dh, "filter": N.FILTERS[f], "filterScale": fw, "exact": exact})
+                ref = Image({"width": dw, "height": dh, "pixel": PIXEL_NAMES[p], "stride": want.shape[1], "data": want.reshape(-1).copy()})
+                assert_resize_close(got, ref, exact, ("vec", k, p, f, sw, sh, dw, dh, fw))
+        else:
+            sp, dp, w, h, wi = (int(v) for v in row[2:7])
+            ss = int(row[9])
+            img = Image({"width": w, "height": h, "pixel": PIXEL_NAMES[sp], "stride": ss, "data": ref_vectors[f"cc{k}_src"].copy()})
+            opts = {"pixel": PIXEL_NAMES[dp]}
+            if weights[wi]:
+                opts.update(redWeight=weights[wi][0], greenWeight=weights[wi][1], blueWeight=weights[wi][2])
+            got = P.colorConvertSync(img, opts)
+            assert np.array_equal(got.rows(), ref_vectors[f"cc{k}_dst"]), ("vec cc", k, sp, dp, wi)
+
+
+# ---- colour conversion: all 64 pairs, bit-exact ----------------------------------------------
+
+@pytest.mark.parametrize("sp", range(8))
+def test_color_convert_all_pairs_bit_exact(gpu, sp):
+    P = gpu
+    rng = np.random.default_rng(100 + sp)
+    # 300 px: two full 128-pixel warp steps + a tail; 128: exactly one step; 5: tail only
+    for dp, (w, h, pad, off) in itertools.product(range(8), [(300, 9, 0, 0), (128, 3, 8, 0), (5, 4, 0, 0), (131, 5, 0, 3)]):
+        img = rand_image(rng, w, h, PIXEL_NAMES[sp], pad, off)
+        want, ws = O.color_convert(np.ascontiguousarray(img.data), img.stride, w, h, sp, dp)
+        got = P.colorConvertSync(img, {"pixel": PIXEL_NAMES[dp]})
+        assert np.array_equal(got.rows(), O.payload(want, ws, w, h, dp)), (sp, dp, w, h, pad, off)
+
+
+def test_color_convert_exhaustive_values(gpu):
+    """Every u8 and u16 channel value through the depth-changing and luma paths."""
+    P = gpu
+    v16 = np.arange(65536, dtype=np.uint16)
+    img = Image({"width": 65536, "height": 1, "pixel": "r16", "data": v16.view(np.uint8).copy()})
+    for to in ("grey", "greya", "rgb", "r16g16b16a16", "rgba"):
+        want, ws = O.color_convert(img.data, img.stride, 65536, 1, "r16", to)
+        assert np.array_equal(P.colorConvertSync(img, {"pixel": to}).rows(), O.payload(want, ws, 65536, 1, to)), to
+    v8 = np.arange(256, dtype=np.uint8)
+    img = Image({"width": 256, "height": 1, "pixel": "grey", "data": v8.copy()})
+    for to in ("r16", "r16g16", "r16g16b16", "r16g16b16a16", "rgba"):
+        want, ws = O.color_convert(img.data, img.stride, 256, 1, "grey", to)
+        assert np.array_equal(P.colorConvertSync(img, {"pixel": to}).rows(), O.payload(want, ws, 256, 1, to)), to
+    # luma over a dense lattice of (r, g, b): FMA contraction would flip some of these (SURVEY item 4)
+    r, g, b = np.meshgrid(np.arange(0, 256, 3), np.arange(0, 256, 5), np.arange(0, 256, 7), indexing="ij")
+    px = np.stack([r, g, b], -1).astype(np.uint8).reshape(-1, 3)
+    img = Image({"width": px.shape[0], "height": 1, "pixel": "rgb", "data": np.concatenate([px.reshape(-1), np.zeros(3, np.uint8)])})
+    for to, wts in itertools.product(("grey", "r16"), (None, (0.2126, 0.7152, 0.0722))):
+        opts = {"pixel": to}
+        ow = None
+        if wts:
+            opts.update(redWeight=wts[0], greenWeight=wts[1], blueWeight=wts[2])
+            ow = O.resolve_color_settings(*wts)
+        want, ws = O.color_convert(np.ascontiguousarray(img.data), img.stride, img.width, 1, "rgb", to, ow)
+        assert np.array_equal(P.colorConvertSync(img, opts).rows(), O.payload(want, ws, img.width, 1, to)), (to, wts)
+
+
+def test_color_convert_1080p_cfg2(gpu):
+    """BASELINE cfg2: 1080p rgba -> rgb / grey / greya, bit-exact on every payload byte."""
+    P = gpu
+    w, h = 1920, 1080
+    img = Image({"width": w, "height": h, "pixel": "rgba", "data": fill_host(w, h, 4, w * 4, 1236, 0)})
+    for to in ("rgb", "grey", "greya"):
+        want, ws = O.color_convert(img.data, img.stride, w, h, "rgba", to)
+        got = P.colorConvertSync(img, {"pixel": to})
+        assert np.array_equal(got.rows(), O.payload(want, ws, w, h, to)), to
+
+
+def test_convert_leaves_padding_untouched_and_handles_subviews(gpu):
+    P = gpu
+    rng = np.random.default_rng(3)
+    parent = rand_image(rng, 200, 40, "rgb")
+    view = parent.subView(7, 3, 150, 30)          # byte offset 3*600+21: unaligned base, parent stride
+    want, ws = O.color_convert(np.ascontiguousarray(view.data), view.stride, 150, 30, "rgb", "rgba")
+    got = P.colorConvertSync(view, {"pixel": "rgba"})
+    assert np.array_equal(got.rows(), O.payload(want, ws, 150, 30, "rgba"))
+    # C-ABI with a pre-filled dst whose stride has padding: padding bytes must survive
+    src = rand_image(rng, 33, 6, "rgba")
+    dst_buf = np.full(6 * 40, 0xAB, np.uint8)
+    s = N.CImage(src.data.ctypes.data, src.stride, 33, 6, 1)
+    d = N.CImage(dst_buf.ctypes.data, 40, 33, 6, 2)   # grey, 33 payload + 7 padding
+    assert N.lib.picha_b200_color_convert(ctypes.byref(s), ctypes.byref(d), *O.resolve_color_settings()) == 0
+    rows = dst_buf.reshape(6, 40)
+    assert (rows[:, 33:] == 0xAB).all()
+    want, ws = O.color_convert(src.data, src.stride, 33, 6, "rgba", "grey")
+    assert np.array_equal(rows[:, :33], O.payload(want, ws, 33, 6, "grey"))
+
+
+# ---- resize -----------------------------------------------------------------------------------
+
+SHAPES = [
+    (64, 48, 16, 12, 1.0),     # 4x down: lanczos has 17 taps against a 16-row ring
+    (61, 47, 17, 13, 1.0),     # ragged down
+    (16, 12, 48, 40, 0.7),     # up
+    (40, 20, 20, 10, 1.0),     # 2x: box ring aliasing
+    (30, 30, 10, 10, 1.0),     # 3x: box ring aliasing
+    (33, 21, 47, 9, 1.5),      # up in x, down in y
+    (23, 17, 23, 17, 1.0),     # same size
+    (5, 300, 5, 4, 1.0),       # 75x vertical
+    (300, 5, 4, 5, 1.0),       # 75x horizontal
+    (1, 1, 7, 5, 1.0),         # single source pixel
+    (9, 9, 1, 1, 1.0),         # single destination pixel
+    (50, 50, 100, 100, 0.7),   # README example / cfg1
+    (12, 12, 5, 7, 2.5),
+]
+
+
+@pytest.mark.parametrize("filt", N.FILTERS)
+def test_resize_all_filters_formats_shapes(gpu, filt):
+    P = gpu
+    rng = np.random.default_rng(500 + N.FILTERS.index(filt))
+    for pixel, (sw, sh, dw, dh, fw) in itertools.product(PIXEL_NAMES, SHAPES):
+        img = rand_image(rng, sw, sh, pixel, pad=4 if (sw + dh) % 2 else 0)
+        want = oracle_resize(img, dw, dh, filt, fw)
+        for exact in (True, False):
+            got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw, "exact": exact})
+            assert_resize_close(got, want, exact, (filt, pixel, sw, sh, dw, dh, fw))
+
+
+def test_resize_structured_inputs(gpu):
+    """Constant rows, ramps, 0/max extremes, impulse (SURVEY 8d parity set)."""
+    P = gpu
+    w, h = 96, 64
+    cases = {}
+    cases["zeros"] = np.zeros((h, w, 4), np.uint8)
+    cases["max"] = np.full((h, w, 4), 255, np.uint8)
+    ramp = np.zeros((h, w, 4), np.uint8); ramp[:] = (np.arange(w) * 255 // (w - 1))[None, :, None]
+    cases["ramp"] = ramp
+    imp = np.zeros((h, w, 4), np.uint8); imp[31, 47] = 255
+    cases["impulse"] = imp
+    chk = np.zeros((h, w, 4), np.uint8); chk[::2, ::2] = 255; chk[1::2, 1::2] = 255
+    cases["checker"] = chk
+    for name, arr in cases.items():
+        img = Image({"width": w, "height": h, "pixel": "rgba", "data": arr.reshape(-1).copy()})
+        for filt, (dw, dh) in itertools.product(("lanczos", "cubic", "box", "mitchel"), [(24, 16), (33, 21), (192, 128)]):
+            want = oracle_resize(img, dw, dh, filt, 1.0)
+            for exact in (True, False):
+                got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "exact": exact})
+                assert_resize_close(got, want, exact, (name, filt, dw, dh))
+
+
+def test_resize_subview_and_padding(gpu):
+    P = gpu
+    rng = np.random.default_rng(11)
+    parent = rand_image(rng, 120, 90, "rgb")
+    view = parent.subView(5, 7, 100, 64)
+    want = oracle_resize(view, 31, 19, "cubic", 0.7)
+    assert_resize_close(P.resizeSync(view, {"width": 31, "height": 19, "exact": True}), want, True, "subview")
+    assert_resize_close(P.resizeSync(view, {"width": 31, "height": 19}), want, False, "subview")
+    dst_buf = np.full(19 * 100, 0xCD, np.uint8)
+    s = N.CImage(view.data.ctypes.data, view.stride, 100, 64, 0)
+    d = N.CImage(dst_buf.ctypes.data, 100, 31, 19, 0)
+    assert N.lib.picha_b200_resize(ctypes.byref(s), ctypes.byref(d), 0, np.float32(0.7)) == 0
+    rows = dst_buf.reshape(19, 100)
+    assert (rows[:, 93:] == 0xCD).all()
+    assert np.abs(rows[:, :93].astype(int) - want.rows().astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg4", "cfg5"])
+def test_resize_benchmark_shapes(gpu, cfg):
+    """One synthetic image of each BASELINE resize shape against the oracle (full size)."""
+    P = gpu
+    sw, sh, dw, dh, pixel, filt, opts, seed = {
+        "cfg3": (3840, 2160, 960, 540, "rgba", "lanczos", {"filter": "lanczos"}, 1237),
+        "cfg4": (2048, 2048, 4096, 4096, "r16g16b16a16", "mitchel", {"filter": "mitchel"}, 1238),
+        "cfg5": (1920, 1080, 256, 256, "rgb", "cubic", {}, 1239),
+    }[cfg]
+    bpp = O.PIXEL_BYTES[O.PIXELS.index(pixel)]
+    img = Image({"width": sw, "height": sh, "pixel": pixel, "data": fill_host(sw, sh, bpp, sw * bpp, seed, 0)})
+    fw = 1.0 if "filter" in opts else 0.70
+    want = oracle_resize(img, dw, dh, filt, fw)
+    got = P.resizeSync(img, dict(opts, width=dw, height=dh))
+    assert_resize_close(got, want, False, cfg)
+    if cfg != "cfg4":
+        assert_resize_close(P.resizeSync(img, dict(opts, width=dw, height=dh, exact=True)), want, True, cfg)
+
+
+def test_resize_properties_at_full_size(gpu):
+    """Size-independent properties at BASELINE's full shapes: a constant image stays constant
+    (weights are normalised), and resizing is deterministic call to call."""
+    P = gpu
+    for pixel, sw, sh, dw, dh, filt, val in [("rgba", 3840, 2160, 960, 540, "lanczos", 200),
+                                             ("rgb", 1920, 1080, 256, 256, "cubic", 37)]:
+        img = Image({"width": sw, "height": sh, "pixel": pixel})
+        img.data[:] = val
+        out = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt})
+        assert np.abs(out.rows().astype(int) - val).max() <= 1
+        again = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt})
+        assert out.equalPixels(again)
+
+
+# ---- batches, device-resident entry points, threads -------------------------------------------
+
+def test_batch_matches_single_calls(gpu):
+    P = gpu
+    rng = np.random.default_rng(21)
+    imgs = [rand_image(rng, 160, 120, "rgba") for _ in range(9)]
+    singles = [P.resizeSync(im, {"width": 40, "height": 30, "filter": "lanczos"}) for im in imgs]
+    for device in (0, -1):
+        batch = P.resizeBatchSync(imgs, {"width": 40, "height": 30, "filter": "lanczos"}, device=device)
+        assert all(a.equalPixels(b) for a, b in zip(singles, batch))
+    cs = [P.colorConvertSync(im, {"pixel": "grey"}) for im in imgs]
+    cb = P.colorConvertBatchSync(imgs, {"pixel": "grey"}, device=-1)
+    assert all(a.equalPixels(b) for a, b in zip(cs, cb))
+    assert P.resizeBatchSync([], {"width": 4, "height": 4}) == []
+
+
+def test_device_resident_batch_and_synthetic_parity(gpu):
+    import torch
+    from picha_b200 import device as D
+    n, sw, sh, dw, dh = 5, 512, 256, 128, 64
+    src = D.DeviceBatch(n, sw, sh, "rgba")
+    src.fill_synthetic(1237, first_image=3)
+    torch.cuda.synchronize()
+    for i in (0, 4):
+        host = fill_host(sw, sh, 4, src.stride, 1237, 3 + i)
+        assert np.array_equal(src.image(i).rows(), Image({"width": sw, "height": sh, "pixel": "rgba", "stride": src.stride, "data": host}).rows())
+    dst = D.DeviceBatch(n, dw, dh, "rgba")
+    D.resize(src, dst, "lanczos")
+    grey = D.DeviceBatch(n, sw, sh, "greya")
+    D.color_convert(src, grey)
+    torch.cuda.synchronize()
+    for i in range(n):
+        im = src.image(i)
+        assert_resize_close(dst.image(i), oracle_resize(im, dw, dh, "lanczos", 1.0), False, ("device", i))
+        want, ws = O.color_convert(np.ascontiguousarray(im.data), im.stride, sw, sh, "rgba", "greya")
+        assert np.array_equal(grey.image(i).rows(), O.payload(want, ws, sw, sh, "greya"))
+
+
+def test_pinned_host_buffers(gpu):
+    """Buffers from picha_b200_host_alloc take the no-staging path and give the same bytes."""
+    P = gpu
+    rng = np.random.default_rng(31)
+    img = rand_image(rng, 200, 100, "rgba")
+    n = img.data.size
+    p = N.lib.picha_b200_host_alloc(n)
+    q = N.lib.picha_b200_host_alloc(50 * 25 * 4)
+    assert p and q
+    try:
+        pin_src = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_ubyte)), shape=(n,))
+        pin_dst = np.ctypeslib.as_array(ctypes.cast(q, ctypes.POINTER(ctypes.c_ubyte)), shape=(50 * 25 * 4,))
+        pin_src[:] = img.data
+        s = N.CImage(p, img.stride, 200, 100, 1)
+        d = N.CImage(q, 200, 50, 25, 1)
+        assert N.lib.picha_b200_resize(ctypes.byref(s), ctypes.byref(d), 1, 1.0) == 0
+        want = P.resizeSync(img, {"width": 50, "height": 25, "filter": "lanczos"})
+        assert np.array_equal(pin_dst.reshape(25, 200), want.rows())
+    finally:
+        N.lib.picha_b200_host_free(p)
+        N.lib.picha_b200_host_free(q)
+
+
+def test_concurrent_calls_from_threads(gpu):
+    """picha.resize runs on libuv pool threads, several at once (src/resize.cc:362-364)."""
+    P = gpu
+    rng = np.random.default_rng(41)
+    imgs = [rand_image(rng, 97 + 3 * i, 61 + i, PIXEL_NAMES[i % 8]) for i in range(16)]
+    want = [P.resizeSync(im, {"width": 31, "height": 17}) for im in imgs]
+    got = [None] * len(imgs)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = P.resizeSync(imgs[i], {"width": 31, "height": 17})
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(imgs))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    assert all(a.equalPixels(b) for a, b in zip(want, got))

@@ -1,0 +1,53 @@
+"""The N>1 path on CPU: two gloo ranks shard a batch by image (no data-path collective) and
+agree on the max-over-ranks step time the way bench.py does."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from picha_b200.shard import shard_range
+    import bench
+    n = 37
+    lo, hi = shard_range(n, rank, world)
+    owned = torch.zeros(n, dtype=torch.int64)
+    owned[lo:hi] = 1
+    dist.all_reduce(owned)                      # test-only: every image is owned exactly once
+    ms = bench.max_over_ranks(10.0 + rank)      # what bench.py reports as the step time
+    total = bench.sum_over_ranks(hi - lo)
+    q.put((rank, owned.tolist(), ms, total))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_by_image_and_take_max_time():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, owned, ms, total in res:
+        assert owned == [1] * 37
+        assert ms == 11.0
+        assert total == 37
