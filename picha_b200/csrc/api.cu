@@ -89,6 +89,8 @@ struct Plan {
 	AxisTable x, y;
 	uint32_t *blob = nullptr;   // device
 	ResizeTables t{};
+	FastTables ft{};            // tile_w / band_h are filled per launch
+	int fast_tile_w[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
 	~Plan() { if (blob) cudaFree(blob); }
 };
 
@@ -222,6 +224,23 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	size_t o_blo = put_i(blo), o_brows = put_i(brows);
 	size_t o_xw = put_f(p->x.w), o_yw = put_f(p->y.w);
 
+	// fast path tables (vertical axis as accumulator ring / row window, horizontal axis padded)
+	FastAxisY fy;
+	FastAxisX fx;
+	build_fast_y(p->y, kFastMaxDepth, fy);
+	build_fast_x(p->x, fx);
+	while (blob.size() % 4) blob.push_back(0);   // float4 loads of the vertical weight rows
+	size_t o_fwv = put_f(fy.wv);
+	size_t o_fxw = put_f(fx.w);
+	size_t o_cum = put_i(fy.cum), o_smin = put_i(fy.smin), o_ybase = put_i(fy.ybase), o_lo = put_i(fy.lo);
+	for (int px = 0; px < kNumPixels; ++px) {
+		const PixelInfo pi = pixel_info(px);
+		int unit = 16;
+		while (unit > 1 && (unit / 2 * pi.bytes) % 16 == 0) unit /= 2;   // tile starts stay 16-byte aligned
+		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
+			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 256);
+	}
+
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
 	CU(cudaMemcpy(p->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
 	const int *ib = reinterpret_cast<const int *>(p->blob);
@@ -232,6 +251,11 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->t.xw = fb + o_xw; p->t.yw = fb + o_yw;
 	p->t.band_h = band_h;
 	p->t.max_band_rows = max_rows;
+	p->ft.xfirst = ib + o_xfirst; p->ft.xcount = ib + o_xcount;
+	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
+	p->ft.variant = fy.variant; p->ft.depth = fy.depth; p->ft.ystride = fy.stride;
+	p->ft.cum = ib + o_cum; p->ft.smin = ib + o_smin; p->ft.ybase = ib + o_ybase; p->ft.lo = ib + o_lo;
+	p->ft.wv = fb + o_fwv;
 
 	dev->plans[key] = p;
 	dev->lru.push_front(key);
@@ -354,9 +378,26 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	std::shared_ptr<Plan> plan;
 	int rc = get_plan(dev, tag, width, s.width, s.height, d.width, d.height, &plan);
 	if (rc) return rc;
-	(void)flags;
 	int launches = 0;
-	cudaError_t e = launch_resize_exact(s, d, n, plan->t, stream, &launches);
+	cudaError_t e = cudaErrorNotSupported;
+	if (!(flags & PICHA_B200_EXACT) && plan->fast_tile_w[s.pixel] > 0) {
+		FastTables ft = plan->ft;
+		ft.tile_w = plan->fast_tile_w[s.pixel];
+		// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, full-height
+		// strips (no vertical halo) when it is large; band heights are multiples of 8 rows.
+		const long long tiles = (long long)((d.width + ft.tile_w - 1) / ft.tile_w) * n;
+		long long bands = (148LL * 4 * 16 + tiles - 1) / tiles;
+		const int max_bands = d.height / 16 > 0 ? d.height / 16 : 1;
+		if (bands > max_bands) bands = max_bands;
+		if (bands < 1) bands = 1;
+		ft.band_h = (int)(((d.height + bands - 1) / bands + 7) / 8 * 8);
+		e = launch_resize_fast(s, d, n, ft, stream, &launches);
+		if (e == cudaErrorNotSupported) cudaGetLastError();
+	}
+	if (e == cudaErrorNotSupported) {
+		launches = 0;
+		e = launch_resize_exact(s, d, n, plan->t, stream, &launches);
+	}
 	g_launches += launches;
 	if (e == cudaErrorInvalidValue) { cudaGetLastError(); return PICHA_B200_ERR_UNSUPPORTED; }
 	if (e != cudaSuccess) return fail_cuda(e, "resize kernel launch");

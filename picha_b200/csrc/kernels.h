@@ -38,6 +38,34 @@ cudaError_t launch_resize_exact(const DevBatch &src, const DevBatch &dst, int n,
 cudaError_t launch_color_convert(const DevBatch &src, const DevBatch &dst, int n,
                                  float rf, float gf, float bf, cudaStream_t stream, int *launches);
 
+// Device-resident tables of the fast resize path (see tables.h: FastAxisY / FastAxisX).
+struct FastTables {
+	const int *xfirst, *xcount;
+	const float *xw;
+	int xstride;
+	int variant, depth, ystride;
+	const int *cum, *smin, *ybase, *lo;
+	const float *wv;
+	int tile_w;   // output columns per CTA
+	int band_h;   // output rows per CTA
+};
+
+constexpr int kFastThreads = 128;        // threads per CTA = source column groups per tile
+constexpr int kFastValuesPerThread = 8;  // channel values of one source row owned by a thread
+constexpr int kFastMaxDepth = 12;
+
+// Largest tile width (output columns, a multiple of `unit`) whose source span fits one CTA row
+// for every tile; 0 if none does.
+int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap);
+
+// Fused two-pass resize for throughput: TMA-staged source rows, vertical pass in registers with
+// thread-private columns, horizontal pass from shared memory, coalesced stores. FMA arithmetic,
+// vertical-then-horizontal order: within +-1 LSB of the reference, not bit-exact.
+// Needs 16-byte aligned source base / stride / step (TMA). Returns cudaErrorNotSupported when the
+// shape or alignment is outside what it handles (the caller then uses the exact kernel).
+cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &t,
+                               cudaStream_t stream, int *launches);
+
 cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uint64_t first_image,
                                   cudaStream_t stream, int *launches);
 

@@ -115,4 +115,72 @@ void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTab
 		}
 }
 
+void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
+	f = FastAxisY();
+	const int n = t.dst_size;
+	std::vector<int> first(n), last(n);
+	for (int y = 0; y < n; ++y) {
+		int lo = t.src_size, hi = -1;
+		for (int k = 0; k < t.count[y]; ++k) {
+			int r = t.eff[t.start[y] + k];
+			if (r < lo) lo = r;
+			if (r > hi) hi = r;
+		}
+		first[y] = lo;
+		last[y] = hi;
+	}
+	f.cum.resize(n);
+	f.smin.resize(n);
+	for (int y = 0, m = -1; y < n; ++y) { if (last[y] > m) m = last[y]; f.cum[y] = m; }
+	for (int y = n - 1, m = t.src_size; y >= 0; --y) { if (first[y] < m) m = first[y]; f.smin[y] = m; }
+	f.lo = f.smin;
+
+	// kDown: which output is open when row r arrives
+	f.ybase.assign(t.src_size, n);
+	for (int r = 0, y = 0; r < t.src_size; ++r) {
+		while (y < n && f.cum[y] < r) ++y;
+		f.ybase[r] = y;
+	}
+	int need_down = 0, need_up = 0;
+	for (int y = 0; y < n; ++y) {
+		for (int k = 0; k < t.count[y]; ++k) {
+			int d = y - f.ybase[t.eff[t.start[y] + k]] + 1;
+			if (d > need_down) need_down = d;
+		}
+		int span = last[y] - f.lo[y] + 1;
+		if (span > need_up) need_up = span;
+	}
+	const bool down_ok = need_down <= max_depth, up_ok = need_up <= max_depth;
+	if (!down_ok && !up_ok) return;
+	// the form with the smaller register footprint; ties go with the direction of the scale
+	bool use_down = down_ok && (!up_ok || need_down < need_up || (need_down == need_up && t.scale >= 1.0f));
+	f.variant = use_down ? FastAxisY::kDown : FastAxisY::kUp;
+	f.depth = use_down ? need_down : need_up;
+	f.stride = (f.depth + 3) & ~3;
+	if (use_down) {
+		f.wv.assign(size_t(t.src_size) * f.stride, 0.0f);
+		for (int y = 0; y < n; ++y)
+			for (int k = 0; k < t.count[y]; ++k) {
+				int r = t.eff[t.start[y] + k];
+				f.wv[size_t(r) * f.stride + (y - f.ybase[r])] += t.w[t.start[y] + k];
+			}
+	} else {
+		f.wv.assign(size_t(n) * f.stride, 0.0f);
+		for (int y = 0; y < n; ++y)
+			for (int k = 0; k < t.count[y]; ++k) {
+				int r = t.eff[t.start[y] + k];
+				f.wv[size_t(y) * f.stride + (r - f.lo[y])] += t.w[t.start[y] + k];
+			}
+	}
+}
+
+void build_fast_x(const AxisTable &t, FastAxisX &f) {
+	f = FastAxisX();
+	f.taps = t.max_taps;
+	f.stride = t.max_taps | 1;
+	f.w.assign(size_t(t.dst_size) * f.stride, 0.0f);
+	for (int x = 0; x < t.dst_size; ++x)
+		for (int k = 0; k < t.count[x]; ++k) f.w[size_t(x) * f.stride + k] = t.w[t.start[x] + k];
+}
+
 }  // namespace picha_b200

@@ -38,6 +38,34 @@ struct AxisTable {
 	std::vector<int> need;        // needrow(i), resize.cc:104
 };
 
+// Vertical axis re-expressed for the fast kernel's first pass, where every thread owns a few
+// source columns and walks down the rows (csrc/resize_fast.cu).  Two equivalent forms of the same
+// banded matrix (taps that alias to one effective row are merged by adding their weights):
+//   kDown  "accumulator ring": source row r adds wv[r*stride + j] * value into output
+//          ybase[r] + j, j < depth; output y is complete once rows <= cum[y] are consumed.
+//   kUp    "row window": output y = sum_k wv[y*stride + k] * value(row lo[y] + k), k < depth.
+// All arrays are band-independent, so the launch may cut the image into bands of any height.
+struct FastAxisY {
+	enum { kNone = -1, kDown = 0, kUp = 1 };
+	int variant = kNone;
+	int depth = 0;    // accumulators (kDown) or window rows (kUp) needed
+	int stride = 0;   // depth rounded up to a multiple of 4 (float4 loads)
+	std::vector<int> cum;    // [dst] running max of the last effective row of outputs <= y
+	std::vector<int> smin;   // [dst] first effective row touched by any output >= y
+	std::vector<int> ybase;  // [src] kDown: first output still open when row r is consumed
+	std::vector<int> lo;     // [dst] kUp: window base (= smin)
+	std::vector<float> wv;
+};
+void build_fast_y(const AxisTable &y, int max_depth, FastAxisY &out);
+
+// Horizontal axis for the second pass: weights padded to a fixed row length.
+struct FastAxisX {
+	int taps = 0;            // max taps of any output column
+	int stride = 0;          // odd row length >= taps (bank-conflict-free in shared memory)
+	std::vector<float> w;    // [dst][stride]
+};
+void build_fast_x(const AxisTable &x, FastAxisX &out);
+
 // Filter tag order: src/resize.cc:151-160.  `width` is ResizeOptions::width (ScaledFilter scale).
 void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTable &out);
 
