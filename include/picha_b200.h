@@ -83,7 +83,9 @@ enum picha_b200_status {
 };
 
 /* Flags for the *_ex / *_device entry points. */
-#define PICHA_B200_EXACT 1u   /* resize: force the bit-exact kernel (reference summation order, no FMA) */
+#define PICHA_B200_EXACT 1u       /* resize: force the bit-exact kernel (reference summation order, no FMA) */
+#define PICHA_B200_FORCE_FAST 2u  /* resize: use the throughput kernel whenever it supports the shape, even for
+                                     images so small that the default picks the bit-exact kernel (tests) */
 
 /* ---- library ------------------------------------------------------------------------- */
 

@@ -31,6 +31,7 @@ ERR_UNSUPPORTED = -11
 ERR_INVALID_ARGUMENT = -12
 
 EXACT = 1
+FORCE_FAST = 2
 
 
 class CImage(ctypes.Structure):

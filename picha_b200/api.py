@@ -112,7 +112,9 @@ def _prepare_resize(img, opts):
         raise N.PichaError(N.ERR_INVALID_DIMENSIONS)
     tag, fwidth = _resize_options(opts)
     out, dst = _new_image(width, height, src.pixel)
-    flags = N.EXACT if _get(opts, "exact") else 0
+    # extensions to picha's option object: exact=True forces the bit-exact kernel, fast=True the
+    # throughput kernel (by default small images get the former, large ones the latter)
+    flags = N.EXACT if _get(opts, "exact") else (N.FORCE_FAST if _get(opts, "fast") else 0)
     return src, keep, out, dst, tag, fwidth, flags
 
 

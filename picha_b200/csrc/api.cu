@@ -94,6 +94,14 @@ struct Plan {
 	~Plan() { if (blob) cudaFree(blob); }
 };
 
+// Smallest pixel count whose byte size is a multiple of 16: tile origins (source TMA boxes) and
+// tile widths (destination vector stores) are multiples of it.
+int align_pixels(int bytes_per_pixel) {
+	int unit = 16;
+	while (unit > 1 && (unit / 2 * bytes_per_pixel) % 16 == 0) unit /= 2;
+	return unit;
+}
+
 typedef std::tuple<int, uint32_t, int, int, int, int> PlanKey;   // filter, width bits, sw, sh, dw, dh
 
 // A lane is what one in-flight host call owns: a stream, staging and device scratch.
@@ -235,8 +243,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	size_t o_cum = put_i(fy.cum), o_smin = put_i(fy.smin), o_ybase = put_i(fy.ybase), o_lo = put_i(fy.lo);
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
-		int unit = 16;
-		while (unit > 1 && (unit / 2 * pi.bytes) % 16 == 0) unit /= 2;   // tile starts stay 16-byte aligned
+		const int unit = align_pixels(pi.bytes);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
 			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 256);
 	}
@@ -380,9 +387,14 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	if (rc) return rc;
 	int launches = 0;
 	cudaError_t e = cudaErrorNotSupported;
-	if (!(flags & PICHA_B200_EXACT) && plan->fast_tile_w[s.pixel] > 0) {
+	// Small images are launch-latency bound either way, so they get the bit-exact kernel; the
+	// throughput kernel (within +-1 LSB) takes everything large enough for bandwidth to matter.
+	const bool large = (long long)s.width * s.height >= 128 * 128 &&
+	                   (long long)d.width * d.height * pixel_info(d.pixel).channels >= 4096;
+	if (!(flags & PICHA_B200_EXACT) && (large || (flags & PICHA_B200_FORCE_FAST)) && plan->fast_tile_w[s.pixel] > 0) {
 		FastTables ft = plan->ft;
 		ft.tile_w = plan->fast_tile_w[s.pixel];
+		ft.align_px = align_pixels(pixel_info(s.pixel).bytes);
 		// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, full-height
 		// strips (no vertical halo) when it is large; band heights are multiples of 8 rows.
 		const long long tiles = (long long)((d.width + ft.tile_w - 1) / ft.tile_w) * n;

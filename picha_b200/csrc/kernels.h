@@ -47,6 +47,7 @@ struct FastTables {
 	const int *cum, *smin, *ybase, *lo;
 	const float *wv;
 	int tile_w;   // output columns per CTA
+	int align_px; // tile source origins are multiples of this many pixels (16-byte TMA start)
 	int band_h;   // output rows per CTA
 };
 

@@ -279,7 +279,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	c.img = blockIdx.z;
 	c.x0 = blockIdx.x * t.tile_w;
 	c.tw = min(t.tile_w, dst.width - c.x0);
-	c.sx0 = t.xfirst[c.x0] & ~3;                      // tile origin: a whole word for any format
+	c.sx0 = t.xfirst[c.x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
 	c.word0 = c.sx0 * bpp / 4;
 
 	const int y0 = blockIdx.y * t.band_h, y1 = min(dst.height, y0 + t.band_h);
@@ -466,7 +466,7 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 			int lo = xfirst[x0];
 			for (int x = x0; x <= x1; ++x)
 				if (xfirst[x] < lo) lo = xfirst[x];
-			if (lo != xfirst[x0] || hi - (xfirst[x0] & ~3) > limit) ok = false;
+			if (lo != xfirst[x0] || hi - xfirst[x0] / unit * unit > limit) ok = false;
 		}
 		if (ok) return tw;
 	}

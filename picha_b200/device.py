@@ -55,7 +55,7 @@ class DeviceBatch:
         view[:, :rows.shape[1]] = rows.to(self.device)
 
 
-def resize(src, dst, filter="cubic", filter_scale=None, exact=False):
+def resize(src, dst, filter="cubic", filter_scale=None, exact=False, fast=False):
     """dst[i] = resizeImage(src[i]) for every image of the batch, on the current stream."""
     tag_out, width_out = ctypes.c_int(0), ctypes.c_float(0)
     has_filter = filter is not None
@@ -66,7 +66,8 @@ def resize(src, dst, filter="cubic", filter_scale=None, exact=False):
     s, d = src.cimage(), dst.cimage()
     with torch.cuda.device(src.device):
         N.check(N.lib.picha_b200_resize_device(src.n, ctypes.byref(s), src.step, ctypes.byref(d), dst.step,
-                                               tag_out.value, width_out.value, N.EXACT if exact else 0,
+                                               tag_out.value, width_out.value,
+                                               N.EXACT if exact else (N.FORCE_FAST if fast else 0),
                                                torch.cuda.current_stream().cuda_stream))
 
 

@@ -20,6 +20,8 @@ pytestmark = pytest.mark.gpu
 
 MAX_LSB = 1
 MEAN_LSB = 0.05
+# the bit-exact kernel, the default choice, and the throughput kernel forced onto small images
+MODES = [{"exact": True}, {}, {"fast": True}]
 
 
 def rand_image(rng, w, h, pixel, pad=0, offset=0):
@@ -40,12 +42,19 @@ def oracle_resize(img, dw, dh, filt, fw):
 
 
 def assert_resize_close(got, want, exact, ctx):
+    """exact: identical.  Otherwise max |diff| <= 1 step and mean |diff| <= 0.05 steps (u8 steps, or
+    u16 steps for the r16* formats).  On outputs of fewer than 4096 values a single off-by-one would
+    already break the mean, so there the mean bound reads "at most max(1, 5 %) of the values differ"."""
     a, b = chan(got).astype(np.int64), chan(want).astype(np.int64)
     d = np.abs(a - b)
     if exact:
         assert d.max() == 0, (ctx, "exact mode differs", int(d.max()), float(d.mean()))
+        return
+    assert d.max() <= MAX_LSB, (ctx, int(d.max()), float(d.mean()))
+    if d.size >= 4096:
+        assert d.mean() <= MEAN_LSB, (ctx, int(d.max()), float(d.mean()))
     else:
-        assert d.max() <= MAX_LSB and d.mean() <= MEAN_LSB, (ctx, int(d.max()), float(d.mean()))
+        assert int((d > 0).sum()) <= max(1, int(MEAN_LSB * d.size)), (ctx, int((d > 0).sum()), d.size)
 
 
 # ---- the reference's own tests, transliterated -------------------------------------------------
@@ -116,10 +125,10 @@ def test_committed_reference_vectors(gpu, ref_vectors):
             fw, ss = float(row[8]), int(row[9])
             img = Image({"width": sw, "height": sh, "pixel": PIXEL_NAMES[p], "stride": ss, "data": ref_vectors[f"rs{k}_src"].copy()})
             want = ref_vectors[f"rs{k}_dst"]
-            for exact in (True, False):
-                got = P.resizeSync(img, {"width": dw, "height": dh, "filter": N.FILTERS[f], "filterScale": fw, "exact": exact})
-                ref = Image({"width": dw, "height": dh, "pixel": PIXEL_NAMES[p], "stride": want.shape[1], "data": want.reshape(-1).copy()})
-                assert_resize_close(got, ref, exact, ("vec", k, p, f, sw, sh, dw, dh, fw))
+            ref = Image({"width": dw, "height": dh, "pixel": PIXEL_NAMES[p], "stride": want.shape[1], "data": want.reshape(-1).copy()})
+            for mode in MODES:
+                got = P.resizeSync(img, dict({"width": dw, "height": dh, "filter": N.FILTERS[f], "filterScale": fw}, **mode))
+                assert_resize_close(got, ref, mode.get("exact", False), ("vec", k, p, f, sw, sh, dw, dh, fw, mode))
         else:
             sp, dp, w, h, wi = (int(v) for v in row[2:7])
             ss = int(row[9])
@@ -229,9 +238,24 @@ def test_resize_all_filters_formats_shapes(gpu, filt):
     for pixel, (sw, sh, dw, dh, fw) in itertools.product(PIXEL_NAMES, SHAPES):
         img = rand_image(rng, sw, sh, pixel, pad=4 if (sw + dh) % 2 else 0)
         want = oracle_resize(img, dw, dh, filt, fw)
-        for exact in (True, False):
-            got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw, "exact": exact})
-            assert_resize_close(got, want, exact, (filt, pixel, sw, sh, dw, dh, fw))
+        for mode in MODES:
+            got = P.resizeSync(img, dict({"width": dw, "height": dh, "filter": filt, "filterScale": fw}, **mode))
+            assert_resize_close(got, want, mode.get("exact", False), (filt, pixel, sw, sh, dw, dh, fw, mode))
+
+
+@pytest.mark.parametrize("pixel", PIXEL_NAMES)
+def test_resize_fast_kernel_multi_tile(gpu, pixel):
+    """Medium images: several column tiles and row bands per image, so tile origins, halos and the
+    TMA box starts of every pixel size are exercised (the throughput kernel is the default here)."""
+    P = gpu
+    rng = np.random.default_rng(900 + PIXEL_NAMES.index(pixel))
+    for (sw, sh, dw, dh, filt, fw) in [(1000, 400, 251, 97, "lanczos", 1.0), (777, 333, 200, 111, "cubic", 0.7),
+                                       (301, 203, 640, 410, "mitchel", 1.0), (640, 360, 640, 90, "triangle", 1.0),
+                                       (500, 500, 125, 250, "box", 1.0), (400, 300, 533, 100, "catmulrom", 1.3)]:
+        img = rand_image(rng, sw, sh, pixel)
+        want = oracle_resize(img, dw, dh, filt, fw)
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        assert_resize_close(got, want, False, (pixel, sw, sh, dw, dh, filt, fw))
 
 
 def test_resize_structured_inputs(gpu):
@@ -251,9 +275,9 @@ def test_resize_structured_inputs(gpu):
         img = Image({"width": w, "height": h, "pixel": "rgba", "data": arr.reshape(-1).copy()})
         for filt, (dw, dh) in itertools.product(("lanczos", "cubic", "box", "mitchel"), [(24, 16), (33, 21), (192, 128)]):
             want = oracle_resize(img, dw, dh, filt, 1.0)
-            for exact in (True, False):
-                got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "exact": exact})
-                assert_resize_close(got, want, exact, (name, filt, dw, dh))
+            for mode in MODES:
+                got = P.resizeSync(img, dict({"width": dw, "height": dh, "filter": filt}, **mode))
+                assert_resize_close(got, want, mode.get("exact", False), (name, filt, dw, dh, mode))
 
 
 def test_resize_subview_and_padding(gpu):
@@ -264,6 +288,7 @@ def test_resize_subview_and_padding(gpu):
     want = oracle_resize(view, 31, 19, "cubic", 0.7)
     assert_resize_close(P.resizeSync(view, {"width": 31, "height": 19, "exact": True}), want, True, "subview")
     assert_resize_close(P.resizeSync(view, {"width": 31, "height": 19}), want, False, "subview")
+    assert_resize_close(P.resizeSync(view, {"width": 31, "height": 19, "fast": True}), want, False, "subview fast")
     dst_buf = np.full(19 * 100, 0xCD, np.uint8)
     s = N.CImage(view.data.ctypes.data, view.stride, 100, 64, 0)
     d = N.CImage(dst_buf.ctypes.data, 100, 31, 19, 0)
