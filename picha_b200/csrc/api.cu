@@ -403,6 +403,9 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 		if (bands > max_bands) bands = max_bands;
 		if (bands < 1) bands = 1;
 		ft.band_h = (int)(((d.height + bands - 1) / bands + 7) / 8 * 8);
+		// the band's vertical index table (and, for the row-window form, its weights) live in shared memory
+		const int band_cap = ft.variant == 0 ? 1024 : 256;
+		if (ft.band_h > band_cap) ft.band_h = band_cap;
 		e = launch_resize_fast(s, d, n, ft, stream, &launches);
 		if (e == cudaErrorNotSupported) cudaGetLastError();
 	}

@@ -44,21 +44,28 @@ constexpr int G = 8;               // output rows per pass-2 group
 constexpr int TMPS = NT * NV + 4;  // floats per intermediate row (+4: rows land 4 banks apart)
 
 struct SmemLayout {
-	int row_bytes;   // bytes per staged source row
-	int ring, tmp, out, out_stride, xw, xf, xc, bars, total;
+	int row_bytes;    // bytes per staged source row
+	int wstage;       // kDown: bytes of vertical weights travelling with each stage
+	int ring, wring, tmp, out, out_stride, xw, xf, xc, ytab, ywt, bars, total;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp, int xstride) {
+// band_rows: entries of the per-band vertical index table (cum[] for kDown, lo[] for kUp).
+__host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp, int xstride, int variant, int ystride,
+                                                  int band_rows) {
 	SmemLayout L;
 	L.row_bytes = NT * NV * (deep ? 2 : 1);
+	L.wstage = variant == 0 ? RS * ystride * 4 : 0;
 	L.ring = 0;
-	L.tmp = L.ring + NS * RS * L.row_bytes;
+	L.wring = L.ring + NS * RS * L.row_bytes;
+	L.tmp = L.wring + NS * L.wstage;
 	L.out = L.tmp + G * TMPS * 4;
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + G * L.out_stride;
 	L.xf = L.xw + tile_w * xstride * 4;
 	L.xc = L.xf + tile_w * 4;
-	L.bars = ((L.xc + tile_w * 4 + 7) / 8) * 8;
+	L.ytab = L.xc + tile_w * 4;
+	L.ywt = ((L.ytab + band_rows * 4 + 15) / 16) * 16;
+	L.bars = L.ywt + (variant == 0 ? 0 : band_rows * ystride * 4);
 	L.total = L.bars + NS * 8;
 	return L;
 }
@@ -86,6 +93,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 	asm volatile(
 		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
 		::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+// Contiguous bytes (a multiple of 16, 16-byte aligned on both sides) into shared memory.
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile(
+		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- unpack: exact float(v) * (1/max) in one FMA ----------------------------------------------
@@ -117,146 +130,114 @@ template <bool DEEP> __device__ __forceinline__ unsigned pack_fast(float f) {
 	return (unsigned)t;
 }
 
-// Everything a CTA keeps about its tile.
-struct Tile {
-	const CUtensorMap *map;
-	uint8_t *smem;
-	SmemLayout L;
-	uint64_t *bars;
-	int tid;
-	int word0, row0, img;     // TMA coordinates of the tile's first staged row
-	int nstages;              // stages the tile consumes
-	int stage, stage_row;     // consumer position
-	// pass 2
-	const FastTables *t;
-	DevBatch dst;
-	uint8_t *dimg;
-	int x0, tw, sx0;
-};
-
-template <bool DEEP> __device__ __forceinline__ void issue_stage(const Tile &c, int k) {
-	constexpr int BOXES = DEEP ? 2 : 1;   // TMA boxes are at most 256 elements wide
-	uint64_t *bar = c.bars + (k % NS);
-	mbar_expect_tx(bar, RS * c.L.row_bytes);
-	uint8_t *dst = c.smem + c.L.ring + (k % NS) * RS * c.L.row_bytes;
+template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint8_t *d, const float *acc) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	if (BPP == 4 && !DEEP) {
+		*reinterpret_cast<uint32_t *>(d) = pack_fast<false>(acc[0]) | (pack_fast<false>(acc[1 % C]) << 8) |
+		                                   (pack_fast<false>(acc[2 % C]) << 16) | (pack_fast<false>(acc[3 % C]) << 24);
+	} else if (BPP == 8) {
+		*reinterpret_cast<uint2 *>(d) = make_uint2(pack_fast<true>(acc[0]) | (pack_fast<true>(acc[1 % C]) << 16),
+		                                           pack_fast<true>(acc[2 % C]) | (pack_fast<true>(acc[3 % C]) << 16));
+	} else if (DEEP) {
 #pragma unroll
-	for (int b = 0; b < BOXES; ++b)
-		tma_load_3d(dst + b * RS * 1024, c.map, bar, c.word0 + b * 256, c.row0 + k * RS, c.img);
-}
-
-// Next source row of the tile for this thread: its words in the ring (waits for the stage).
-template <bool DEEP> __device__ __forceinline__ const uint32_t *next_row(Tile &c) {
-	constexpr int WPT = DEEP ? 4 : 2;
-	if (c.stage_row == RS) {          // uniform: every thread has finished the previous stage
-		__syncthreads();
-		++c.stage;
-		if (c.tid == 0 && c.stage + NS - 1 < c.nstages) issue_stage<DEEP>(c, c.stage + NS - 1);
-		mbar_wait(c.bars + (c.stage % NS), (c.stage / NS) & 1);
-		c.stage_row = 0;
-	}
-	const int word = c.tid * WPT;     // a DEEP row is two 256-word boxes, each [RS][256]
-	const uint8_t *base = c.smem + c.L.ring + (c.stage % NS) * RS * c.L.row_bytes;
-	const uint32_t *p = reinterpret_cast<const uint32_t *>(base) + (DEEP ? (word >> 8) * RS * 256 : 0) +
-	                    c.stage_row * 256 + (word & 255);
-	++c.stage_row;
-	return p;
-}
-
-template <bool DEEP> __device__ __forceinline__ void load_row(Tile &c, float *u) {
-	const uint32_t *p = next_row<DEEP>(c);
-	uint32_t w[4];
-	if (DEEP) {
-		uint4 v = *reinterpret_cast<const uint4 *>(p);
-		w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+		for (int ch = 0; ch < C; ++ch) reinterpret_cast<uint16_t *>(d)[ch] = (uint16_t)pack_fast<true>(acc[ch]);
 	} else {
-		uint2 v = *reinterpret_cast<const uint2 *>(p);
-		w[0] = v.x; w[1] = v.y;
+#pragma unroll
+		for (int ch = 0; ch < C; ++ch) d[ch] = (uint8_t)pack_fast<false>(acc[ch]);
 	}
-	unpack8<DEEP>(w, u);
-}
-
-__device__ __forceinline__ void emit_row(const Tile &c, int g, const float *v) {
-	float4 *d = reinterpret_cast<float4 *>(c.smem + c.L.tmp) + (g * TMPS + c.tid * NV) / 4;
-	d[0] = make_float4(v[0], v[1], v[2], v[3]);
-	d[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
 // ---- pass 2: horizontal filter of one group of intermediate rows, pack, store --------------------
-template <int C, bool DEEP>
-__device__ __noinline__ void pass2(const Tile &c, int gy0, int ng) {
-	constexpr int BPP = C * Depth<DEEP>::bytes;
-	const float *tmp = reinterpret_cast<const float *>(c.smem + c.L.tmp);
-	const float *sxw = reinterpret_cast<const float *>(c.smem + c.L.xw);
-	const int *sxf = reinterpret_cast<const int *>(c.smem + c.L.xf);
-	const int *sxc = reinterpret_cast<const int *>(c.smem + c.L.xc);
-	uint8_t *outt = c.smem + c.L.out;
-	const int xstride = c.t->xstride;
+// A thread produces the output pixels (xx, g) and (xx, g + 4): the two rows share the x weights.
+// Lanes: g fastest (4 rows), then 8 different xx per warp -- float4 reads of a quarter-warp fall in
+// distinct banks (rows are 4 banks apart, neighbouring columns of a 4:1 downscale 16 banks apart).
+struct Pass2Args {
+	const float *tmp;      // [G][TMPS]
+	const float *xw;       // [tile_w][xstride], zero padded
+	const int *xf, *xc;    // first source pixel (relative to the tile origin), taps
+	uint8_t *outt;         // [G][out_stride]
+	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
+	int xstride, out_stride, dstride, tw, ng, tid;
+};
 
-	for (int o = c.tid; o < c.tw * G; o += NT) {
-		const int g = o & (G - 1), xx = o >> 3;
-		if (g >= ng) continue;
-		const int cnt = sxc[xx];
-		const float *w = sxw + xx * xstride;
-		const float *v = tmp + g * TMPS + sxf[xx] * C;
-		float acc[C];
+template <int C, bool DEEP>
+__device__ __noinline__ void pass2(Pass2Args a) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	for (int o = a.tid; o < a.tw * 4; o += NT) {
+		const int g = o & 3, xx = o >> 2;
+		if (g >= a.ng) continue;
+		const bool two = g + 4 < a.ng;
+		const int cnt = a.xc[xx];
+		const float *w = a.xw + xx * a.xstride;
+		const float *v0 = a.tmp + g * TMPS + a.xf[xx] * C;
+		const float *v1 = v0 + (two ? 4 * TMPS : 0);
+		float acc0[C], acc1[C];
 #pragma unroll
-		for (int ch = 0; ch < C; ++ch) acc[ch] = 0.0f;
+		for (int ch = 0; ch < C; ++ch) acc0[ch] = acc1[ch] = 0.0f;
+		int k = 0;
+		if (C == 4) {
+			for (; k + 4 <= cnt; k += 4) {
+				const float4 wq = *reinterpret_cast<const float4 *>(w + k);
+				const float wk[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const float4 p = *reinterpret_cast<const float4 *>(v0 + 4 * (k + j));
+					const float4 q = *reinterpret_cast<const float4 *>(v1 + 4 * (k + j));
+					acc0[0] = fmaf(wk[j], p.x, acc0[0]); acc0[1 % C] = fmaf(wk[j], p.y, acc0[1 % C]);
+					acc0[2 % C] = fmaf(wk[j], p.z, acc0[2 % C]); acc0[3 % C] = fmaf(wk[j], p.w, acc0[3 % C]);
+					acc1[0] = fmaf(wk[j], q.x, acc1[0]); acc1[1 % C] = fmaf(wk[j], q.y, acc1[1 % C]);
+					acc1[2 % C] = fmaf(wk[j], q.z, acc1[2 % C]); acc1[3 % C] = fmaf(wk[j], q.w, acc1[3 % C]);
+				}
+			}
+			for (; k < cnt; ++k) {
+				const float wk = w[k];
+				const float4 p = *reinterpret_cast<const float4 *>(v0 + 4 * k);
+				const float4 q = *reinterpret_cast<const float4 *>(v1 + 4 * k);
+				acc0[0] = fmaf(wk, p.x, acc0[0]); acc0[1 % C] = fmaf(wk, p.y, acc0[1 % C]);
+				acc0[2 % C] = fmaf(wk, p.z, acc0[2 % C]); acc0[3 % C] = fmaf(wk, p.w, acc0[3 % C]);
+				acc1[0] = fmaf(wk, q.x, acc1[0]); acc1[1 % C] = fmaf(wk, q.y, acc1[1 % C]);
+				acc1[2 % C] = fmaf(wk, q.z, acc1[2 % C]); acc1[3 % C] = fmaf(wk, q.w, acc1[3 % C]);
+			}
+		} else {
 #pragma unroll 4
-		for (int k = 0; k < cnt; ++k) {
-			const float wk = w[k];
-			if (C == 4) {
-				float4 p = *reinterpret_cast<const float4 *>(v + 4 * k);
-				acc[0] = fmaf(wk, p.x, acc[0]); acc[1] = fmaf(wk, p.y, acc[1]);
-				acc[2 % C] = fmaf(wk, p.z, acc[2 % C]); acc[3 % C] = fmaf(wk, p.w, acc[3 % C]);
-			} else if (C == 2) {
-				float2 p = *reinterpret_cast<const float2 *>(v + 2 * k);
-				acc[0] = fmaf(wk, p.x, acc[0]); acc[1 % C] = fmaf(wk, p.y, acc[1 % C]);
-			} else {
+			for (; k < cnt; ++k) {
+				const float wk = w[k];
 #pragma unroll
-				for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(wk, v[C * k + ch], acc[ch]);
+				for (int ch = 0; ch < C; ++ch) {
+					acc0[ch] = fmaf(wk, v0[C * k + ch], acc0[ch]);
+					acc1[ch] = fmaf(wk, v1[C * k + ch], acc1[ch]);
+				}
 			}
 		}
-		uint8_t *d = outt + g * c.L.out_stride + xx * BPP;
-		if (BPP == 4 && !DEEP) {
-			*reinterpret_cast<uint32_t *>(d) = pack_fast<false>(acc[0]) | (pack_fast<false>(acc[1 % C]) << 8) |
-			                                   (pack_fast<false>(acc[2 % C]) << 16) | (pack_fast<false>(acc[3 % C]) << 24);
-		} else if (BPP == 8) {
-			*reinterpret_cast<uint2 *>(d) = make_uint2(pack_fast<true>(acc[0]) | (pack_fast<true>(acc[1 % C]) << 16),
-			                                           pack_fast<true>(acc[2 % C]) | (pack_fast<true>(acc[3 % C]) << 16));
-		} else if (DEEP) {
-#pragma unroll
-			for (int ch = 0; ch < C; ++ch) reinterpret_cast<uint16_t *>(d)[ch] = (uint16_t)pack_fast<true>(acc[ch]);
-		} else {
-#pragma unroll
-			for (int ch = 0; ch < C; ++ch) d[ch] = (uint8_t)pack_fast<false>(acc[ch]);
-		}
+		uint8_t *d = a.outt + g * a.out_stride + xx * BPP;
+		store_pixel<C, DEEP>(d, acc0);
+		if (two) store_pixel<C, DEEP>(d + 4 * a.out_stride, acc1);
 	}
 	__syncthreads();
 
 	// shared-memory tile -> global, 16 bytes per thread where the destination allows it
-	const int row_bytes = c.tw * BPP;
-	uint8_t *gbase = c.dimg + (long long)gy0 * c.dst.stride + (long long)c.x0 * BPP;
-	const bool vec = ((reinterpret_cast<uintptr_t>(gbase) | (uintptr_t)c.dst.stride) & 15) == 0;
+	const int row_bytes = a.tw * BPP;
+	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
 	const int nvec = vec ? row_bytes >> 4 : 0;
-	for (int i = c.tid; i < ng * nvec; i += NT) {
+	for (int i = a.tid; i < a.ng * nvec; i += NT) {
 		const int g = i / nvec, j = i - g * nvec;
-		reinterpret_cast<uint4 *>(gbase + (long long)g * c.dst.stride)[j] =
-			reinterpret_cast<const uint4 *>(outt + g * c.L.out_stride)[j];
+		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] =
+			reinterpret_cast<const uint4 *>(a.outt + g * a.out_stride)[j];
 	}
 	const int tail0 = nvec << 4, tail = row_bytes - tail0;
-	for (int i = c.tid; i < ng * tail; i += NT) {
+	for (int i = a.tid; i < a.ng * tail; i += NT) {
 		const int g = i / tail, j = tail0 + (i - g * tail);
-		gbase[(long long)g * c.dst.stride + j] = outt[g * c.L.out_stride + j];
+		a.gbase[(long long)g * a.dstride + j] = a.outt[g * a.out_stride + j];
 	}
 }
 
-template <bool DEEP> __device__ __forceinline__ void run_pass2(const Tile &c, int channels, int gy0, int ng) {
+template <bool DEEP> __device__ __forceinline__ void run_pass2(const Pass2Args &a, int channels) {
 	__syncthreads();           // the group's intermediate rows are complete
 	switch (channels) {
-		case 1: pass2<1, DEEP>(c, gy0, ng); break;
-		case 2: pass2<2, DEEP>(c, gy0, ng); break;
-		case 3: pass2<3, DEEP>(c, gy0, ng); break;
-		default: pass2<4, DEEP>(c, gy0, ng); break;
+		case 1: pass2<1, DEEP>(a); break;
+		case 2: pass2<2, DEEP>(a); break;
+		case 3: pass2<3, DEEP>(a); break;
+		default: pass2<4, DEEP>(a); break;
 	}
 	__syncthreads();           // pass 1 may overwrite the intermediate rows again
 }
@@ -265,47 +246,116 @@ template <int VARIANT, int DEPTH, bool DEEP>
 __global__ void __launch_bounds__(NT)
 resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t, int channels) {
 	extern __shared__ __align__(128) uint8_t smem[];
+	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
+	constexpr int WS = (DEPTH + 3) & ~3;         // vertical weights per row, padded for float4
 	const int bpp = channels * Depth<DEEP>::bytes;
+	const int tid = threadIdx.x;
 
-	Tile c;
-	c.map = &smap;
-	c.smem = smem;
-	c.L = smem_layout(DEEP, t.tile_w, bpp, t.xstride);
-	c.bars = reinterpret_cast<uint64_t *>(smem + c.L.bars);
-	c.tid = threadIdx.x;
-	c.t = &t;
-	c.dst = dst;
-	c.dimg = dst.base + (long long)blockIdx.z * dst.step;
-	c.img = blockIdx.z;
-	c.x0 = blockIdx.x * t.tile_w;
-	c.tw = min(t.tile_w, dst.width - c.x0);
-	c.sx0 = t.xfirst[c.x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
-	c.word0 = c.sx0 * bpp / 4;
-
+	const int x0 = blockIdx.x * t.tile_w;
+	const int tw = min(t.tile_w, dst.width - x0);
+	const int sx0 = t.xfirst[x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
+	const int word0 = sx0 * bpp / 4;
 	const int y0 = blockIdx.y * t.band_h, y1 = min(dst.height, y0 + t.band_h);
 	const int rlo = t.smin[y0], rhi = t.cum[y1 - 1];
-	c.row0 = rlo;
-	c.nstages = (rhi - rlo + RS) / RS;
-	c.stage = -1;
-	c.stage_row = RS;
+	const int nstages = (rhi - rlo + RS) / RS;
+	const int ys = VARIANT == 0 ? t.ybase[rlo] : y0;           // kDown starts at the output open at row rlo (<= y0)
 
-	if (c.tid == 0) {
-		for (int i = 0; i < NS; ++i) mbar_init(c.bars + i, 1);
+	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride, VARIANT, t.ystride, t.band_h + kFastMaxDepth);
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+	const int *ytab = reinterpret_cast<const int *>(smem + L.ytab);
+
+	auto issue_stage = [&](int k) {
+		constexpr int BOXES = DEEP ? 2 : 1;      // TMA boxes are at most 256 elements wide
+		uint64_t *bar = bars + (k % NS);
+		mbar_expect_tx(bar, RS * L.row_bytes + L.wstage);
+		uint8_t *d = smem + L.ring + (k % NS) * RS * L.row_bytes;
+#pragma unroll
+		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RS * 1024, &smap, bar, word0 + b * 256, rlo + k * RS, blockIdx.z);
+		if (VARIANT == 0)
+			bulk_load_1d(smem + L.wring + (k % NS) * L.wstage, t.wv + (long long)(rlo + k * RS) * t.ystride, L.wstage, bar);
+	};
+
+	if (tid == 0) {
+		for (int i = 0; i < NS; ++i) mbar_init(bars + i, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		for (int k = 0; k < NS - 1 && k < c.nstages; ++k) issue_stage<DEEP>(c, k);
+		for (int k = 0; k < NS - 1 && k < nstages; ++k) issue_stage(k);
 	}
-	// this tile's horizontal tables -> shared memory
+	// this tile's horizontal tables and this band's vertical tables -> shared memory
 	{
-		float *sxw = reinterpret_cast<float *>(smem + c.L.xw);
-		int *sxf = reinterpret_cast<int *>(smem + c.L.xf), *sxc = reinterpret_cast<int *>(smem + c.L.xc);
-		for (int i = c.tid; i < c.tw * t.xstride; i += NT) sxw[i] = t.xw[(long long)c.x0 * t.xstride + i];
-		for (int i = c.tid; i < c.tw; i += NT) {
-			sxf[i] = t.xfirst[c.x0 + i] - c.sx0;
-			sxc[i] = t.xcount[c.x0 + i];
+		float *sxw = reinterpret_cast<float *>(smem + L.xw);
+		int *sxf = reinterpret_cast<int *>(smem + L.xf), *sxc = reinterpret_cast<int *>(smem + L.xc);
+		for (int i = tid; i < tw * t.xstride; i += NT) sxw[i] = t.xw[(long long)x0 * t.xstride + i];
+		for (int i = tid; i < tw; i += NT) {
+			sxf[i] = t.xfirst[x0 + i] - sx0;
+			sxc[i] = t.xcount[x0 + i];
+		}
+		int *sy = reinterpret_cast<int *>(smem + L.ytab);
+		const int *ysrc = VARIANT == 0 ? t.cum : t.lo;
+		for (int i = tid; i < y1 - ys; i += NT) sy[i] = ysrc[ys + i];
+		if (VARIANT == 1) {
+			float *sw = reinterpret_cast<float *>(smem + L.ywt);
+			for (int i = tid; i < (y1 - y0) * t.ystride; i += NT) sw[i] = t.wv[(long long)y0 * t.ystride + i];
 		}
 	}
-	// (the first next_row() starts with a __syncthreads, which also publishes the barriers and tables)
+	// (the first fetch starts with a __syncthreads, which also publishes the barriers and tables)
+
+	// ---- ring consumer: next source row of the tile for this thread (and its vertical weights) ----
+	int stage = -1, stage_row = RS, slot = NS - 1;
+	uint32_t parity = 1;
+	const uint32_t *dptr = nullptr;
+	const float *wptr = nullptr;
+	const int thread_word = (DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255);
+	auto fetch = [&](uint32_t (&w)[WPT], float (&wt)[WS]) {
+		if (stage_row == RS) {            // uniform: every thread has finished the previous stage
+			__syncthreads();
+			++stage;
+			if (++slot == NS) { slot = 0; parity ^= 1; }
+			if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
+			mbar_wait(bars + slot, parity);
+			stage_row = 0;
+			dptr = reinterpret_cast<const uint32_t *>(smem + L.ring + slot * RS * L.row_bytes) + thread_word;
+			wptr = reinterpret_cast<const float *>(smem + L.wring + slot * L.wstage);
+		}
+		if (DEEP) {
+			const uint4 v = *reinterpret_cast<const uint4 *>(dptr);
+			w[0] = v.x; w[1] = v.y; w[2 % WPT] = v.z; w[3 % WPT] = v.w;
+		} else {
+			const uint2 v = *reinterpret_cast<const uint2 *>(dptr);
+			w[0] = v.x; w[1] = v.y;
+		}
+		dptr += 256;
+		if (VARIANT == 0) {
+#pragma unroll
+			for (int q = 0; q < WS / 4; ++q) {
+				const float4 v = reinterpret_cast<const float4 *>(wptr)[q];
+				wt[4 * q] = v.x; wt[4 * q + 1] = v.y; wt[4 * q + 2] = v.z; wt[4 * q + 3] = v.w;
+			}
+			wptr += t.ystride;
+		}
+		++stage_row;
+	};
+
+	Pass2Args pa;
+	pa.tmp = reinterpret_cast<const float *>(smem + L.tmp);
+	pa.xw = reinterpret_cast<const float *>(smem + L.xw);
+	pa.xf = reinterpret_cast<const int *>(smem + L.xf);
+	pa.xc = reinterpret_cast<const int *>(smem + L.xc);
+	pa.outt = smem + L.out;
+	pa.xstride = t.xstride; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid;
+	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * bpp;
+	float4 *const my_tmp = reinterpret_cast<float4 *>(smem + L.tmp) + tid * (NV / 4);
+
+	auto emit_row = [&](int g, const float *v) {
+		float4 *d = my_tmp + g * (TMPS / 4);
+		d[0] = make_float4(v[0], v[1], v[2], v[3]);
+		d[1] = make_float4(v[4], v[5], v[6], v[7]);
+	};
+	auto flush_group = [&](int y_end, int gcount) {      // rows [y_end - gcount, y_end) are in the group buffer
+		pa.ng = gcount;
+		pa.gbase = dtile + (long long)(y_end - gcount) * dst.stride;
+		run_pass2<DEEP>(pa, channels);
+	};
 
 	int gcount = 0;
 	if (VARIANT == 0) {
@@ -314,65 +364,82 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		for (int j = 0; j < DEPTH; ++j)
 #pragma unroll
 			for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
-		int r = rlo;
-		int y = t.ybase[rlo];                           // <= y0: outputs before y0 are not emitted
+		auto accumulate = [&](const uint32_t (&w)[WPT], const float (&wt)[WS], int s) {
+			float u[NV];
+			unpack8<DEEP>(w, u);
+#pragma unroll
+			for (int j = 0; j < DEPTH; ++j)
+#pragma unroll
+				for (int i = 0; i < NV; ++i) acc[(s + j) % DEPTH][i] = fmaf(wt[j], u[i], acc[(s + j) % DEPTH][i]);
+		};
+		// software pipeline: row r+1 is fetched from shared memory before row r is accumulated
+		uint32_t cw[WPT], nw[WPT];
+		float cwt[WS], nwt[WS];
+		int r = rlo, y = ys;
+		fetch(cw, cwt);
 		while (y < y1) {
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					const int need = t.cum[y];
-					for (; r <= need; ++r) {
-						float u[NV];
-						load_row<DEEP>(c, u);
-						const float4 *wp = reinterpret_cast<const float4 *>(t.wv + (long long)r * t.ystride);
-						float w[(DEPTH + 3) & ~3];
+					const int need = ytab[y - ys];
+					while (r <= need) {
+						if (r < rhi) fetch(nw, nwt);
+						accumulate(cw, cwt, s);
+						++r;
+						if (r > need) {
 #pragma unroll
-						for (int q = 0; q < (DEPTH + 3) / 4; ++q) {
-							float4 v = __ldg(wp + q);
-							w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+							for (int i = 0; i < WPT; ++i) cw[i] = nw[i];
+#pragma unroll
+							for (int i = 0; i < WS; ++i) cwt[i] = nwt[i];
+							break;
 						}
-#pragma unroll
-						for (int j = 0; j < DEPTH; ++j)
-#pragma unroll
-							for (int i = 0; i < NV; ++i)
-								acc[(s + j) % DEPTH][i] = fmaf(w[j], u[i], acc[(s + j) % DEPTH][i]);
+						if (r < rhi) fetch(cw, cwt);
+						accumulate(nw, nwt, s);
+						++r;
 					}
 					if (y >= y0) {
-						emit_row(c, gcount, acc[s]);
+						emit_row(gcount, acc[s]);
 						++gcount;
 					}
 #pragma unroll
 					for (int i = 0; i < NV; ++i) acc[s][i] = 0.0f;
 					++y;
 					if (gcount == G || (y == y1 && gcount > 0)) {
-						run_pass2<DEEP>(c, channels, y - gcount, gcount);
+						flush_group(y, gcount);
 						gcount = 0;
 					}
 				}
 			}
 		}
 	} else {
+		const float *ywt = reinterpret_cast<const float *>(smem + L.ywt);
 		float win[DEPTH][NV];
-		int rb = t.lo[y0], rnext = rb;
+		float unused[WS];
+		int rb = ytab[0], rnext = rb;
+		auto load_window_row = [&](float *dstv) {
+			if (rnext <= rhi) {
+				uint32_t w[WPT];
+				fetch(w, unused);
+				unpack8<DEEP>(w, dstv);
+				++rnext;
+			} else {
 #pragma unroll
-		for (int k = 0; k < DEPTH; ++k) {
-			if (rnext <= rhi) { load_row<DEEP>(c, win[k]); ++rnext; }
-			else {
-#pragma unroll
-				for (int i = 0; i < NV; ++i) win[k][i] = 0.0f;
+				for (int i = 0; i < NV; ++i) dstv[i] = 0.0f;
 			}
-		}
+		};
+#pragma unroll
+		for (int k = 0; k < DEPTH; ++k) load_window_row(win[k]);
 		int y = y0;
 		while (y < y1) {
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					while (y < y1 && t.lo[y] == rb) {
-						const float4 *wp = reinterpret_cast<const float4 *>(t.wv + (long long)y * t.ystride);
-						float w[(DEPTH + 3) & ~3];
+					while (y < y1 && ytab[y - y0] == rb) {
+						const float4 *wp = reinterpret_cast<const float4 *>(ywt + (y - y0) * t.ystride);
+						float w[WS];
 #pragma unroll
-						for (int q = 0; q < (DEPTH + 3) / 4; ++q) {
-							float4 v = __ldg(wp + q);
+						for (int q = 0; q < WS / 4; ++q) {
+							const float4 v = wp[q];
 							w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
 						}
 						float o[NV];
@@ -382,20 +449,16 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 						for (int k = 0; k < DEPTH; ++k)
 #pragma unroll
 							for (int i = 0; i < NV; ++i) o[i] = fmaf(w[k], win[(s + k) % DEPTH][i], o[i]);
-						emit_row(c, gcount, o);
+						emit_row(gcount, o);
 						++gcount;
 						++y;
 						if (gcount == G || y == y1) {
-							run_pass2<DEEP>(c, channels, y - gcount, gcount);
+							flush_group(y, gcount);
 							gcount = 0;
 						}
 					}
 					if (y < y1) {                       // slide the window down one source row
-						if (rnext <= rhi) { load_row<DEEP>(c, win[s]); ++rnext; }
-						else {
-#pragma unroll
-							for (int i = 0; i < NV; ++i) win[s][i] = 0.0f;
-						}
+						load_window_row(win[s]);
 						++rb;
 					}
 				}
@@ -404,8 +467,10 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	}
 
 	// Never leave with a TMA load still in flight: wait for every stage that was issued.
-	for (int k = c.stage + 1; k < c.nstages && k < c.stage + NS; ++k)
-		mbar_wait(c.bars + (k % NS), (k / NS) & 1);
+	for (int k = stage + 1; k < nstages && k < stage + NS; ++k) {
+		if (++slot == NS) { slot = 0; parity ^= 1; }
+		mbar_wait(bars + slot, parity);
+	}
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -485,7 +550,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	EncodeTiledFn encode = encode_fn();
 	if (!encode) return cudaErrorNotSupported;
 
-	const SmemLayout L = smem_layout(deep, t.tile_w, bpp, t.xstride);
+	const SmemLayout L = smem_layout(deep, t.tile_w, bpp, t.xstride, t.variant, t.ystride, t.band_h + kFastMaxDepth);
 	if (L.total > max_dynamic_smem()) return cudaErrorNotSupported;
 
 	// The batch as a 3-D tensor of 32-bit words: (words per row, rows, images).

@@ -158,7 +158,8 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 	f.depth = use_down ? need_down : need_up;
 	f.stride = (f.depth + 3) & ~3;
 	if (use_down) {
-		f.wv.assign(size_t(t.src_size) * f.stride, 0.0f);
+		// 8 extra zero rows: the kernel copies the weights of whole 8-row stages
+		f.wv.assign(size_t(t.src_size + 8) * f.stride, 0.0f);
 		for (int y = 0; y < n; ++y)
 			for (int k = 0; k < t.count[y]; ++k) {
 				int r = t.eff[t.start[y] + k];
@@ -177,7 +178,8 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 void build_fast_x(const AxisTable &t, FastAxisX &f) {
 	f = FastAxisX();
 	f.taps = t.max_taps;
-	f.stride = t.max_taps | 1;
+	f.stride = (t.max_taps + 3) & ~3;      // float4 reads; 4 mod 8 keeps 8 neighbouring rows in distinct banks
+	if (f.stride % 8 == 0) f.stride += 4;
 	f.w.assign(size_t(t.dst_size) * f.stride, 0.0f);
 	for (int x = 0; x < t.dst_size; ++x)
 		for (int k = 0; k < t.count[x]; ++k) f.w[size_t(x) * f.stride + k] = t.w[t.start[x] + k];

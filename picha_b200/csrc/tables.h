@@ -61,7 +61,7 @@ void build_fast_y(const AxisTable &y, int max_depth, FastAxisY &out);
 // Horizontal axis for the second pass: weights padded to a fixed row length.
 struct FastAxisX {
 	int taps = 0;            // max taps of any output column
-	int stride = 0;          // odd row length >= taps (bank-conflict-free in shared memory)
+	int stride = 0;          // row length >= taps: a multiple of 4 that is 4 mod 8
 	std::vector<float> w;    // [dst][stride]
 };
 void build_fast_x(const AxisTable &x, FastAxisX &out);

@@ -258,6 +258,31 @@ def test_resize_fast_kernel_multi_tile(gpu, pixel):
         assert_resize_close(got, want, False, (pixel, sw, sh, dw, dh, filt, fw))
 
 
+def axis_matrix(filt, fw, src, dst, vertical):
+    """The reference's filter along one axis as a dense float64 (dst x src) matrix, from the product's
+    own contribution table; the vertical one uses the effective (ring-aliased) rows."""
+    f = N.FILTERS.index(filt)
+    ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+    left = np.zeros(dst, np.int32); count = np.zeros(dst, np.int32); off = np.zeros(dst, np.int32)
+    n = N.lib.picha_b200_contribs(f, fw, src, dst, left.ctypes.data_as(ip), count.ctypes.data_as(ip), off.ctypes.data_as(ip), None, None, 0)
+    w = np.zeros(n, np.float32); eff = np.zeros(n, np.int32)
+    N.lib.picha_b200_contribs(f, fw, src, dst, left.ctypes.data_as(ip), count.ctypes.data_as(ip), off.ctypes.data_as(ip),
+                              w.ctypes.data_as(fp), eff.ctypes.data_as(ip), n)
+    m = np.zeros((dst, src), np.float64)
+    for i in range(dst):
+        for k in range(count[i]):
+            m[i, eff[off[i] + k] if vertical else left[i] + k] += float(w[off[i] + k])
+    return m
+
+
+def real_valued_resize(arr, dw, dh, filt, fw):
+    """(dh, dw, C) float64 result of the reference's separable filter without any rounding."""
+    h, w, _ = arr.shape
+    u = arr.astype(np.float64) / 255.0
+    mx, my = axis_matrix(filt, fw, w, dw, False), axis_matrix(filt, fw, h, dh, True)
+    return np.einsum("yr,rxc->yxc", my, np.einsum("xs,rsc->rxc", mx, u))
+
+
 def test_resize_structured_inputs(gpu):
     """Constant rows, ramps, 0/max extremes, impulse (SURVEY 8d parity set)."""
     P = gpu
@@ -275,9 +300,19 @@ def test_resize_structured_inputs(gpu):
         img = Image({"width": w, "height": h, "pixel": "rgba", "data": arr.reshape(-1).copy()})
         for filt, (dw, dh) in itertools.product(("lanczos", "cubic", "box", "mitchel"), [(24, 16), (33, 21), (192, 128)]):
             want = oracle_resize(img, dw, dh, filt, 1.0)
+            truth = real_valued_resize(arr, dw, dh, filt, 1.0)
             for mode in MODES:
                 got = P.resizeSync(img, dict({"width": dw, "height": dh, "filter": filt}, **mode))
-                assert_resize_close(got, want, mode.get("exact", False), (name, filt, dw, dh, mode))
+                if mode.get("exact"):
+                    assert_resize_close(got, want, True, (name, filt, dw, dh, mode))
+                    continue
+                # These images put many results exactly on a rounding tie (x.5), where the reference's own
+                # choice is decided by its float rounding noise: any implementation that is not bit-identical
+                # may land on the other side, so the mean bound does not apply.  What must hold: at most one
+                # step from the reference, and a correct rounding of the real-valued result.
+                g = got.rows().astype(np.float64).reshape(dh, dw, 4)
+                assert np.abs(g - want.rows().astype(np.float64).reshape(dh, dw, 4)).max() <= 1, (name, filt, dw, dh, mode)
+                assert np.abs(g - np.clip(truth * 255.0, 0, 255)).max() <= 0.5 + 1e-2, (name, filt, dw, dh, mode)
 
 
 def test_resize_subview_and_padding(gpu):
