@@ -80,12 +80,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	uint32_t ok;
+	uint32_t spins = 0;
 	do {
 		asm volatile(
 			"{\n\t.reg .pred p;\n\t"
 			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
 			"selp.u32 %0, 1, 0, p;\n\t}"
 			: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+		// A copy that never lands is a bug in this file, not a condition to wait out: fail the launch
+		// (cudaErrorLaunchFailure reaches the caller as PICHA_B200_ERR_CUDA) instead of hanging the GPU.
+		if (!ok && ++spins > (1u << 24)) __trap();
 	} while (!ok);
 }
 // One box of a 3-D tensor (words, rows, images) into shared memory.
@@ -298,7 +302,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 			for (int i = tid; i < (y1 - y0) * t.ystride; i += NT) sw[i] = t.wv[(long long)y0 * t.ystride + i];
 		}
 	}
-	// (the first fetch starts with a __syncthreads, which also publishes the barriers and tables)
+	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
 	// ---- ring consumer: next source row of the tile for this thread (and its vertical weights) ----
 	int stage = -1, stage_row = RS, slot = NS - 1;
