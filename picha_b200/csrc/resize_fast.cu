@@ -155,14 +155,26 @@ template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint8_t 
 // A thread produces the output pixels (xx, g) and (xx, g + 4): the two rows share the x weights.
 // Lanes: g fastest (4 rows), then 8 different xx per warp -- float4 reads of a quarter-warp fall in
 // distinct banks (rows are 4 banks apart, neighbouring columns of a 4:1 downscale 16 banks apart).
+// (shared-memory locations travel as byte offsets into the CTA's dynamic shared memory so that
+// every access stays an LDS/STS with 32-bit addressing; generic pointers cost a 64-bit add and a
+// generic load each.)
 struct Pass2Args {
-	const float *tmp;      // [G][TMPS]
-	const float *xw;       // [tile_w][xstride], zero padded
-	const int *xf, *xc;    // first source pixel (relative to the tile origin), taps
-	uint8_t *outt;         // [G][out_stride]
+	int tmp;               // float [G][TMPS]
+	int xw;                // float [tile_w][xstride], zero padded
+	int xf, xc;            // int: first source pixel (relative to the tile origin), taps
+	int outt;              // bytes [G][out_stride]
 	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
 	int xstride, out_stride, dstride, tw, ng, tid;
 };
+
+extern __shared__ __align__(128) uint8_t smem[];
+
+template <typename T> __device__ __forceinline__ T lds(int byte_offset) {
+	return *reinterpret_cast<const T *>(smem + byte_offset);
+}
+template <typename T> __device__ __forceinline__ void sts(int byte_offset, const T &v) {
+	*reinterpret_cast<T *>(smem + byte_offset) = v;
+}
 
 template <int C, bool DEEP>
 __device__ __noinline__ void pass2(Pass2Args a) {
@@ -171,22 +183,22 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		const int g = o & 3, xx = o >> 2;
 		if (g >= a.ng) continue;
 		const bool two = g + 4 < a.ng;
-		const int cnt = a.xc[xx];
-		const float *w = a.xw + xx * a.xstride;
-		const float *v0 = a.tmp + g * TMPS + a.xf[xx] * C;
-		const float *v1 = v0 + (two ? 4 * TMPS : 0);
+		const int cnt = lds<int>(a.xc + 4 * xx);
+		const int w = a.xw + 4 * xx * a.xstride;
+		const int v0 = a.tmp + 4 * (g * TMPS + lds<int>(a.xf + 4 * xx) * C);
+		const int v1 = v0 + (two ? 16 * TMPS : 0);
 		float acc0[C], acc1[C];
 #pragma unroll
 		for (int ch = 0; ch < C; ++ch) acc0[ch] = acc1[ch] = 0.0f;
 		int k = 0;
 		if (C == 4) {
 			for (; k + 4 <= cnt; k += 4) {
-				const float4 wq = *reinterpret_cast<const float4 *>(w + k);
+				const float4 wq = lds<float4>(w + 4 * k);
 				const float wk[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
 				for (int j = 0; j < 4; ++j) {
-					const float4 p = *reinterpret_cast<const float4 *>(v0 + 4 * (k + j));
-					const float4 q = *reinterpret_cast<const float4 *>(v1 + 4 * (k + j));
+					const float4 p = lds<float4>(v0 + 16 * (k + j));
+					const float4 q = lds<float4>(v1 + 16 * (k + j));
 					acc0[0] = fmaf(wk[j], p.x, acc0[0]); acc0[1 % C] = fmaf(wk[j], p.y, acc0[1 % C]);
 					acc0[2 % C] = fmaf(wk[j], p.z, acc0[2 % C]); acc0[3 % C] = fmaf(wk[j], p.w, acc0[3 % C]);
 					acc1[0] = fmaf(wk[j], q.x, acc1[0]); acc1[1 % C] = fmaf(wk[j], q.y, acc1[1 % C]);
@@ -194,9 +206,9 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 				}
 			}
 			for (; k < cnt; ++k) {
-				const float wk = w[k];
-				const float4 p = *reinterpret_cast<const float4 *>(v0 + 4 * k);
-				const float4 q = *reinterpret_cast<const float4 *>(v1 + 4 * k);
+				const float wk = lds<float>(w + 4 * k);
+				const float4 p = lds<float4>(v0 + 16 * k);
+				const float4 q = lds<float4>(v1 + 16 * k);
 				acc0[0] = fmaf(wk, p.x, acc0[0]); acc0[1 % C] = fmaf(wk, p.y, acc0[1 % C]);
 				acc0[2 % C] = fmaf(wk, p.z, acc0[2 % C]); acc0[3 % C] = fmaf(wk, p.w, acc0[3 % C]);
 				acc1[0] = fmaf(wk, q.x, acc1[0]); acc1[1 % C] = fmaf(wk, q.y, acc1[1 % C]);
@@ -205,15 +217,15 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		} else {
 #pragma unroll 4
 			for (; k < cnt; ++k) {
-				const float wk = w[k];
+				const float wk = lds<float>(w + 4 * k);
 #pragma unroll
 				for (int ch = 0; ch < C; ++ch) {
-					acc0[ch] = fmaf(wk, v0[C * k + ch], acc0[ch]);
-					acc1[ch] = fmaf(wk, v1[C * k + ch], acc1[ch]);
+					acc0[ch] = fmaf(wk, lds<float>(v0 + 4 * (C * k + ch)), acc0[ch]);
+					acc1[ch] = fmaf(wk, lds<float>(v1 + 4 * (C * k + ch)), acc1[ch]);
 				}
 			}
 		}
-		uint8_t *d = a.outt + g * a.out_stride + xx * BPP;
+		uint8_t *d = smem + a.outt + g * a.out_stride + xx * BPP;
 		store_pixel<C, DEEP>(d, acc0);
 		if (two) store_pixel<C, DEEP>(d + 4 * a.out_stride, acc1);
 	}
@@ -225,13 +237,12 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 	const int nvec = vec ? row_bytes >> 4 : 0;
 	for (int i = a.tid; i < a.ng * nvec; i += NT) {
 		const int g = i / nvec, j = i - g * nvec;
-		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] =
-			reinterpret_cast<const uint4 *>(a.outt + g * a.out_stride)[j];
+		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.outt + g * a.out_stride + 16 * j);
 	}
 	const int tail0 = nvec << 4, tail = row_bytes - tail0;
 	for (int i = a.tid; i < a.ng * tail; i += NT) {
 		const int g = i / tail, j = tail0 + (i - g * tail);
-		a.gbase[(long long)g * a.dstride + j] = a.outt[g * a.out_stride + j];
+		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
 	}
 }
 
@@ -249,7 +260,6 @@ template <bool DEEP> __device__ __forceinline__ void run_pass2(const Pass2Args &
 template <int VARIANT, int DEPTH, bool DEEP>
 __global__ void __launch_bounds__(NT)
 resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t, int channels) {
-	extern __shared__ __align__(128) uint8_t smem[];
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
 	constexpr int WS = (DEPTH + 3) & ~3;         // vertical weights per row, padded for float4
 	const int bpp = channels * Depth<DEEP>::bytes;
@@ -266,7 +276,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 
 	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride, VARIANT, t.ystride, t.band_h + kFastMaxDepth);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-	const int *ytab = reinterpret_cast<const int *>(smem + L.ytab);
+	const int ytab = L.ytab;   // int [band rows]: cum[] (kDown) or lo[] (kUp) of this band
 
 	auto issue_stage = [&](int k) {
 		constexpr int BOXES = DEEP ? 2 : 1;      // TMA boxes are at most 256 elements wide
@@ -305,55 +315,50 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
 	// ---- ring consumer: next source row of the tile for this thread (and its vertical weights) ----
-	int stage = -1, stage_row = RS, slot = NS - 1;
+	int stage = -1, slot = NS - 1;
 	uint32_t parity = 1;
-	const uint32_t *dptr = nullptr;
-	const float *wptr = nullptr;
-	const int thread_word = (DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255);
+	int doff = 0, dend = 0, woff = 0;      // byte offsets of the next row's data / weights; end of the stage
+	const int wrow = t.ystride * 4;
+	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255));
 	auto fetch = [&](uint32_t (&w)[WPT], float (&wt)[WS]) {
-		if (stage_row == RS) {            // uniform: every thread has finished the previous stage
+		if (doff == dend) {               // uniform: every thread has finished the previous stage
 			__syncthreads();
 			++stage;
 			if (++slot == NS) { slot = 0; parity ^= 1; }
 			if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
 			mbar_wait(bars + slot, parity);
-			stage_row = 0;
-			dptr = reinterpret_cast<const uint32_t *>(smem + L.ring + slot * RS * L.row_bytes) + thread_word;
-			wptr = reinterpret_cast<const float *>(smem + L.wring + slot * L.wstage);
+			doff = L.ring + slot * RS * L.row_bytes + thread_byte;
+			dend = doff + RS * 1024;
+			woff = L.wring + slot * L.wstage;
 		}
 		if (DEEP) {
-			const uint4 v = *reinterpret_cast<const uint4 *>(dptr);
+			const uint4 v = lds<uint4>(doff);
 			w[0] = v.x; w[1] = v.y; w[2 % WPT] = v.z; w[3 % WPT] = v.w;
 		} else {
-			const uint2 v = *reinterpret_cast<const uint2 *>(dptr);
+			const uint2 v = lds<uint2>(doff);
 			w[0] = v.x; w[1] = v.y;
 		}
-		dptr += 256;
+		doff += 1024;
 		if (VARIANT == 0) {
 #pragma unroll
 			for (int q = 0; q < WS / 4; ++q) {
-				const float4 v = reinterpret_cast<const float4 *>(wptr)[q];
+				const float4 v = lds<float4>(woff + 16 * q);
 				wt[4 * q] = v.x; wt[4 * q + 1] = v.y; wt[4 * q + 2] = v.z; wt[4 * q + 3] = v.w;
 			}
-			wptr += t.ystride;
+			woff += wrow;
 		}
-		++stage_row;
 	};
 
 	Pass2Args pa;
-	pa.tmp = reinterpret_cast<const float *>(smem + L.tmp);
-	pa.xw = reinterpret_cast<const float *>(smem + L.xw);
-	pa.xf = reinterpret_cast<const int *>(smem + L.xf);
-	pa.xc = reinterpret_cast<const int *>(smem + L.xc);
-	pa.outt = smem + L.out;
+	pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
 	pa.xstride = t.xstride; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid;
 	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * bpp;
-	float4 *const my_tmp = reinterpret_cast<float4 *>(smem + L.tmp) + tid * (NV / 4);
+	const int my_tmp = L.tmp + tid * NV * 4;
 
 	auto emit_row = [&](int g, const float *v) {
-		float4 *d = my_tmp + g * (TMPS / 4);
-		d[0] = make_float4(v[0], v[1], v[2], v[3]);
-		d[1] = make_float4(v[4], v[5], v[6], v[7]);
+		const int d = my_tmp + g * TMPS * 4;
+		sts(d, make_float4(v[0], v[1], v[2], v[3]));
+		sts(d + 16, make_float4(v[4], v[5], v[6], v[7]));
 	};
 	auto flush_group = [&](int y_end, int gcount) {      // rows [y_end - gcount, y_end) are in the group buffer
 		pa.ng = gcount;
@@ -385,7 +390,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					const int need = ytab[y - ys];
+					const int need = lds<int>(ytab + 4 * (y - ys));
 					while (r <= need) {
 						if (r < rhi) fetch(nw, nwt);
 						accumulate(cw, cwt, s);
@@ -416,10 +421,9 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 			}
 		}
 	} else {
-		const float *ywt = reinterpret_cast<const float *>(smem + L.ywt);
 		float win[DEPTH][NV];
 		float unused[WS];
-		int rb = ytab[0], rnext = rb;
+		int rb = lds<int>(ytab), rnext = rb;
 		auto load_window_row = [&](float *dstv) {
 			if (rnext <= rhi) {
 				uint32_t w[WPT];
@@ -438,12 +442,12 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					while (y < y1 && ytab[y - y0] == rb) {
-						const float4 *wp = reinterpret_cast<const float4 *>(ywt + (y - y0) * t.ystride);
+					while (y < y1 && lds<int>(ytab + 4 * (y - y0)) == rb) {
+						const int wp = L.ywt + (y - y0) * wrow;
 						float w[WS];
 #pragma unroll
 						for (int q = 0; q < WS / 4; ++q) {
-							const float4 v = wp[q];
+							const float4 v = lds<float4>(wp + 16 * q);
 							w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
 						}
 						float o[NV];
