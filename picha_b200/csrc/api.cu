@@ -90,6 +90,7 @@ struct Plan {
 	uint32_t *blob = nullptr;   // device
 	ResizeTables t{};
 	FastTables ft{};            // tile_w / band_h are filled per launch
+	FastAxisY fy;               // vertical axis of the fast path (host; sliced into kernel parameters)
 	int fast_tile_w[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
 	~Plan() { if (blob) cudaFree(blob); }
 };
@@ -233,14 +234,11 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	size_t o_xw = put_f(p->x.w), o_yw = put_f(p->y.w);
 
 	// fast path tables (vertical axis as accumulator ring / row window, horizontal axis padded)
-	FastAxisY fy;
+	FastAxisY &fy = p->fy;
 	FastAxisX fx;
 	build_fast_y(p->y, kFastMaxDepth, fy);
 	build_fast_x(p->x, fx);
-	while (blob.size() % 4) blob.push_back(0);   // float4 loads of the vertical weight rows
-	size_t o_fwv = put_f(fy.wv);
 	size_t o_fxw = put_f(fx.w);
-	size_t o_cum = put_i(fy.cum), o_smin = put_i(fy.smin), o_ybase = put_i(fy.ybase), o_lo = put_i(fy.lo);
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
 		const int unit = align_pixels(pi.bytes);
@@ -260,9 +258,6 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->t.max_band_rows = max_rows;
 	p->ft.xfirst = ib + o_xfirst; p->ft.xcount = ib + o_xcount;
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
-	p->ft.variant = fy.variant; p->ft.depth = fy.depth; p->ft.ystride = fy.stride;
-	p->ft.cum = ib + o_cum; p->ft.smin = ib + o_smin; p->ft.ybase = ib + o_ybase; p->ft.lo = ib + o_lo;
-	p->ft.wv = fb + o_fwv;
 
 	dev->plans[key] = p;
 	dev->lru.push_front(key);
@@ -395,18 +390,7 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 		FastTables ft = plan->ft;
 		ft.tile_w = plan->fast_tile_w[s.pixel];
 		ft.align_px = align_pixels(pixel_info(s.pixel).bytes);
-		// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, full-height
-		// strips (no vertical halo) when it is large; band heights are multiples of 8 rows.
-		const long long tiles = (long long)((d.width + ft.tile_w - 1) / ft.tile_w) * n;
-		long long bands = (148LL * 4 * 16 + tiles - 1) / tiles;
-		const int max_bands = d.height / 16 > 0 ? d.height / 16 : 1;
-		if (bands > max_bands) bands = max_bands;
-		if (bands < 1) bands = 1;
-		ft.band_h = (int)(((d.height + bands - 1) / bands + 7) / 8 * 8);
-		// the band's vertical index table (and, for the row-window form, its weights) live in shared memory
-		const int band_cap = ft.variant == 0 ? 1024 : 256;
-		if (ft.band_h > band_cap) ft.band_h = band_cap;
-		e = launch_resize_fast(s, d, n, ft, stream, &launches);
+		e = launch_resize_fast(s, d, n, ft, plan->fy, stream, &launches);
 		if (e == cudaErrorNotSupported) cudaGetLastError();
 	}
 	if (e == cudaErrorNotSupported) {

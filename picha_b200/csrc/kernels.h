@@ -38,14 +38,13 @@ cudaError_t launch_resize_exact(const DevBatch &src, const DevBatch &dst, int n,
 cudaError_t launch_color_convert(const DevBatch &src, const DevBatch &dst, int n,
                                  float rf, float gf, float bf, cudaStream_t stream, int *launches);
 
-// Device-resident tables of the fast resize path (see tables.h: FastAxisY / FastAxisX).
+// Device-resident horizontal tables of the fast resize path (tables.h: FastAxisX); the vertical
+// tables (FastAxisY) stay on the host and travel as kernel parameters, a slice per launch.
 struct FastTables {
 	const int *xfirst, *xcount;
 	const float *xw;
 	int xstride;
-	int variant, depth, ystride;
-	const int *cum, *smin, *ybase, *lo;
-	const float *wv;
+	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA
 	int align_px; // tile source origins are multiples of this many pixels (16-byte TMA start)
 	int band_h;   // output rows per CTA
@@ -59,13 +58,17 @@ constexpr int kFastMaxDepth = 12;
 // for every tile; 0 if none does.
 int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap);
 
+struct FastAxisY;
+
 // Fused two-pass resize for throughput: TMA-staged source rows, vertical pass in registers with
-// thread-private columns, horizontal pass from shared memory, coalesced stores. FMA arithmetic,
-// vertical-then-horizontal order: within +-1 LSB of the reference, not bit-exact.
-// Needs 16-byte aligned source base / stride / step (TMA). Returns cudaErrorNotSupported when the
-// shape or alignment is outside what it handles (the caller then uses the exact kernel).
+// thread-private columns and uniform (constant-bank) weights, horizontal pass from shared memory,
+// coalesced stores. FMA arithmetic, vertical-then-horizontal order: within +-1 LSB of the
+// reference, not bit-exact. Needs 16-byte aligned source base / stride / step (TMA). Returns
+// cudaErrorNotSupported when the shape or alignment is outside what it handles (the caller then
+// uses the exact kernel). One launch per group of row bands whose vertical tables fit the
+// parameter block.
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &t,
-                               cudaStream_t stream, int *launches);
+                               const FastAxisY &fy, cudaStream_t stream, int *launches);
 
 cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uint64_t first_image,
                                   cudaStream_t stream, int *launches);

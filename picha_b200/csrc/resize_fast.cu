@@ -1,21 +1,25 @@
-// Fast fused separable resize for sm_100a (the bandwidth path; reference: src/resize.cc:66-134).
+// Fast fused separable resize for sm_100a (the throughput path; reference: src/resize.cc:66-134).
 //
 // Work split: one CTA (128 threads) produces a tile of `tile_w` x `band_h` output pixels of one
-// image.  The source rows the tile needs are streamed through a 3-stage shared-memory ring by TMA
-// (cp.async.bulk.tensor, one elected thread, mbarrier completion), 8 rows per stage, so global
-// latency is hidden by the copy engine, not by occupancy.
+// image.  The source rows the tile needs are streamed through a shared-memory ring by TMA
+// (cp.async.bulk.tensor, one elected thread, mbarrier completion), so global latency is hidden by
+// the copy engine, not by occupancy.
 //
 // Pass 1 (vertical, in registers).  A thread owns 8 consecutive channel values of the source row
 // (2 words of u8 data, 4 of u16) -- columns are independent in the vertical direction, so every
 // source byte is read from shared memory once, unpacked once, and used for all the output rows it
-// contributes to with warp-uniform weights.  The per-thread state is either
+// contributes to.  The per-thread state is either
 //   kDown  a ring of DEPTH accumulators (one per output row currently open), or
 //   kUp    a window of DEPTH unpacked source rows,
-// rotated by loop unrolling so every register index is static.  Finished rows go to shared
-// memory as floats, 8 output rows per group.
+// rotated by loop unrolling so every register index is static.  The vertical weights and the
+// loop bounds are the same for every thread of the grid, so they travel as a kernel parameter
+// (`VTable`, in the constant bank): the compiler keeps them in uniform registers, the FMAs take
+// the weight as a uniform operand (a third vector-register operand halves the FMA issue rate on
+// this part: tools/microbench/row_body.cu) and all loop control stays on the uniform datapath.
+// Finished rows go to shared memory as floats, G output rows per group.
 //
 // Pass 2 (horizontal, from shared memory).  Each thread takes output pixels of the group; lanes of
-// a quarter-warp walk 8 different rows of the group at the same x, so the float4 reads are
+// a quarter-warp walk different rows of the group at the same x, so the float4 reads are
 // bank-conflict free and the x weights are broadcast.  Results are packed to u8/u16 into a
 // shared-memory tile and leave as 16-byte coalesced row segments.
 //
@@ -29,8 +33,11 @@
 // other (DESIGN.md has the arithmetic).
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 #include "pixel.cuh"
+#include "tables.h"
 
 namespace picha_b200 {
 
@@ -43,31 +50,53 @@ constexpr int NS = 3;              // stages in the ring
 constexpr int G = 8;               // output rows per pass-2 group
 constexpr int TMPS = NT * NV + 4;  // floats per intermediate row (+4: rows land 4 banks apart)
 
+// Vertical tables of one launch, passed by value as a __grid_constant__ kernel parameter (the
+// constant bank holds 32,764 bytes of parameters since CUDA 12.1).  A launch covers the output
+// rows [y_begin, y_end) in bands of band_h rows, one band per blockIdx.y.
+constexpr int kMaxBands = 64;
+constexpr int kYtabMax = 1024;
+constexpr int kWtMax = 5632;
+struct alignas(16) VTable {
+	int y_begin, y_end;
+	int row_base;               // kDown: source row of wt[0]
+	int out_base;               // output row of ytab[0] (and, kUp, of wt[0])
+	int band_rlo[kMaxBands];    // first source row the band touches
+	int band_rhi[kMaxBands];    // last one
+	int band_ys[kMaxBands];     // kDown: output row that is open when row band_rlo arrives (<= the band's first row)
+	int ytab[kYtabMax];         // kDown: cum[out_base + i]; kUp: lo[out_base + i]
+	float wt[kWtMax];           // kDown: weights of source row row_base + i / WS; kUp: of output out_base + i / WS
+};
+static_assert(sizeof(VTable) <= 28 * 1024, "kernel parameters are limited to 32,764 bytes");
+
 struct SmemLayout {
 	int row_bytes;    // bytes per staged source row
-	int wstage;       // kDown: bytes of vertical weights travelling with each stage
-	int ring, wring, tmp, out, out_stride, xw, xf, xc, ytab, ywt, bars, total;
+	int ring, tmp, out, out_stride, xw, xf, xc, bars, total;
 };
 
-// band_rows: entries of the per-band vertical index table (cum[] for kDown, lo[] for kUp).
-__host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp, int xstride, int variant, int ystride,
-                                                  int band_rows) {
+__host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp, int xstride) {
 	SmemLayout L;
 	L.row_bytes = NT * NV * (deep ? 2 : 1);
-	L.wstage = variant == 0 ? RS * ystride * 4 : 0;
 	L.ring = 0;
-	L.wring = L.ring + NS * RS * L.row_bytes;
-	L.tmp = L.wring + NS * L.wstage;
+	L.tmp = L.ring + NS * RS * L.row_bytes;
 	L.out = L.tmp + G * TMPS * 4;
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + G * L.out_stride;
 	L.xf = L.xw + tile_w * xstride * 4;
 	L.xc = L.xf + tile_w * 4;
-	L.ytab = L.xc + tile_w * 4;
-	L.ywt = ((L.ytab + band_rows * 4 + 15) / 16) * 16;
-	L.bars = L.ywt + (variant == 0 ? 0 : band_rows * ystride * 4);
+	L.bars = ((L.xc + tile_w * 4 + 7) / 8) * 8;
 	L.total = L.bars + NS * 8;
 	return L;
+}
+
+extern __shared__ __align__(128) uint8_t smem[];
+
+// Shared-memory locations travel as byte offsets into the CTA's dynamic shared memory so that every
+// access stays an LDS/STS with 32-bit addressing.
+template <typename T> __device__ __forceinline__ T lds(int byte_offset) {
+	return *reinterpret_cast<const T *>(smem + byte_offset);
+}
+template <typename T> __device__ __forceinline__ void sts(int byte_offset, const T &v) {
+	*reinterpret_cast<T *>(smem + byte_offset) = v;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,12 +126,6 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 	asm volatile(
 		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
 		::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
-// Contiguous bytes (a multiple of 16, 16-byte aligned on both sides) into shared memory.
-__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile(
-		"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-		::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // ---- unpack: exact float(v) * (1/max) in one FMA ----------------------------------------------
@@ -155,9 +178,6 @@ template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint8_t 
 // A thread produces the output pixels (xx, g) and (xx, g + 4): the two rows share the x weights.
 // Lanes: g fastest (4 rows), then 8 different xx per warp -- float4 reads of a quarter-warp fall in
 // distinct banks (rows are 4 banks apart, neighbouring columns of a 4:1 downscale 16 banks apart).
-// (shared-memory locations travel as byte offsets into the CTA's dynamic shared memory so that
-// every access stays an LDS/STS with 32-bit addressing; generic pointers cost a 64-bit add and a
-// generic load each.)
 struct Pass2Args {
 	int tmp;               // float [G][TMPS]
 	int xw;                // float [tile_w][xstride], zero padded
@@ -166,15 +186,6 @@ struct Pass2Args {
 	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
 	int xstride, out_stride, dstride, tw, ng, tid;
 };
-
-extern __shared__ __align__(128) uint8_t smem[];
-
-template <typename T> __device__ __forceinline__ T lds(int byte_offset) {
-	return *reinterpret_cast<const T *>(smem + byte_offset);
-}
-template <typename T> __device__ __forceinline__ void sts(int byte_offset, const T &v) {
-	*reinterpret_cast<T *>(smem + byte_offset) = v;
-}
 
 template <int C, bool DEEP>
 __device__ __noinline__ void pass2(Pass2Args a) {
@@ -259,9 +270,10 @@ template <bool DEEP> __device__ __forceinline__ void run_pass2(const Pass2Args &
 
 template <int VARIANT, int DEPTH, bool DEEP>
 __global__ void __launch_bounds__(NT)
-resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t, int channels) {
+resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
+                   const __grid_constant__ VTable vt, int channels) {
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
-	constexpr int WS = (DEPTH + 3) & ~3;         // vertical weights per row, padded for float4
+	constexpr int WS = (DEPTH + 3) & ~3;         // vertical weights per table row
 	const int bpp = channels * Depth<DEEP>::bytes;
 	const int tid = threadIdx.x;
 
@@ -269,24 +281,22 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	const int tw = min(t.tile_w, dst.width - x0);
 	const int sx0 = t.xfirst[x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
 	const int word0 = sx0 * bpp / 4;
-	const int y0 = blockIdx.y * t.band_h, y1 = min(dst.height, y0 + t.band_h);
-	const int rlo = t.smin[y0], rhi = t.cum[y1 - 1];
+	// everything below is uniform across the CTA and comes from the constant bank
+	const int band = blockIdx.y;
+	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
+	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
 	const int nstages = (rhi - rlo + RS) / RS;
-	const int ys = VARIANT == 0 ? t.ybase[rlo] : y0;           // kDown starts at the output open at row rlo (<= y0)
 
-	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride, VARIANT, t.ystride, t.band_h + kFastMaxDepth);
+	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
-	const int ytab = L.ytab;   // int [band rows]: cum[] (kDown) or lo[] (kUp) of this band
 
 	auto issue_stage = [&](int k) {
 		constexpr int BOXES = DEEP ? 2 : 1;      // TMA boxes are at most 256 elements wide
 		uint64_t *bar = bars + (k % NS);
-		mbar_expect_tx(bar, RS * L.row_bytes + L.wstage);
+		mbar_expect_tx(bar, RS * L.row_bytes);
 		uint8_t *d = smem + L.ring + (k % NS) * RS * L.row_bytes;
 #pragma unroll
 		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RS * 1024, &smap, bar, word0 + b * 256, rlo + k * RS, blockIdx.z);
-		if (VARIANT == 0)
-			bulk_load_1d(smem + L.wring + (k % NS) * L.wstage, t.wv + (long long)(rlo + k * RS) * t.ystride, L.wstage, bar);
 	};
 
 	if (tid == 0) {
@@ -295,42 +305,32 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 		for (int k = 0; k < NS - 1 && k < nstages; ++k) issue_stage(k);
 	}
-	// this tile's horizontal tables and this band's vertical tables -> shared memory
-	{
-		float *sxw = reinterpret_cast<float *>(smem + L.xw);
-		int *sxf = reinterpret_cast<int *>(smem + L.xf), *sxc = reinterpret_cast<int *>(smem + L.xc);
-		for (int i = tid; i < tw * t.xstride; i += NT) sxw[i] = t.xw[(long long)x0 * t.xstride + i];
-		for (int i = tid; i < tw; i += NT) {
-			sxf[i] = t.xfirst[x0 + i] - sx0;
-			sxc[i] = t.xcount[x0 + i];
-		}
-		int *sy = reinterpret_cast<int *>(smem + L.ytab);
-		const int *ysrc = VARIANT == 0 ? t.cum : t.lo;
-		for (int i = tid; i < y1 - ys; i += NT) sy[i] = ysrc[ys + i];
-		if (VARIANT == 1) {
-			float *sw = reinterpret_cast<float *>(smem + L.ywt);
-			for (int i = tid; i < (y1 - y0) * t.ystride; i += NT) sw[i] = t.wv[(long long)y0 * t.ystride + i];
-		}
+	// this tile's horizontal tables -> shared memory
+	for (int i = tid; i < tw * t.xstride; i += NT) sts(L.xw + 4 * i, t.xw[(long long)x0 * t.xstride + i]);
+	for (int i = tid; i < tw; i += NT) {
+		sts(L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
+		sts(L.xc + 4 * i, t.xcount[x0 + i]);
 	}
 	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
-	// ---- ring consumer: next source row of the tile for this thread (and its vertical weights) ----
-	int stage = -1, slot = NS - 1;
+	// ---- ring consumer -------------------------------------------------------------------------
+	int stage = -1, slot = NS - 1, rows_left = 0;   // uniform
 	uint32_t parity = 1;
-	int doff = 0, dend = 0, woff = 0;      // byte offsets of the next row's data / weights; end of the stage
-	const int wrow = t.ystride * 4;
+	int doff = 0;                                   // byte offset of this thread's words in the next row
 	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255));
-	auto fetch = [&](uint32_t (&w)[WPT], float (&wt)[WS]) {
-		if (doff == dend) {               // uniform: every thread has finished the previous stage
-			__syncthreads();
-			++stage;
-			if (++slot == NS) { slot = 0; parity ^= 1; }
-			if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
-			mbar_wait(bars + slot, parity);
-			doff = L.ring + slot * RS * L.row_bytes + thread_byte;
-			dend = doff + RS * 1024;
-			woff = L.wring + slot * L.wstage;
-		}
+	auto next_stage = [&]() {
+		__syncthreads();                  // every thread has finished the previous stage
+		++stage;
+		if (++slot == NS) { slot = 0; parity ^= 1; }
+		if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
+		mbar_wait(bars + slot, parity);
+		rows_left = RS;
+		doff = L.ring + slot * RS * L.row_bytes + thread_byte;
+	};
+	auto load_row = [&](float (&u)[NV]) {
+		if (rows_left == 0) next_stage();
+		--rows_left;
+		uint32_t w[WPT];
 		if (DEEP) {
 			const uint4 v = lds<uint4>(doff);
 			w[0] = v.x; w[1] = v.y; w[2 % WPT] = v.z; w[3 % WPT] = v.w;
@@ -339,14 +339,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 			w[0] = v.x; w[1] = v.y;
 		}
 		doff += 1024;
-		if (VARIANT == 0) {
-#pragma unroll
-			for (int q = 0; q < WS / 4; ++q) {
-				const float4 v = lds<float4>(woff + 16 * q);
-				wt[4 * q] = v.x; wt[4 * q + 1] = v.y; wt[4 * q + 2] = v.z; wt[4 * q + 3] = v.w;
-			}
-			woff += wrow;
-		}
+		unpack8<DEEP>(w, u);
 	};
 
 	Pass2Args pa;
@@ -373,39 +366,30 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		for (int j = 0; j < DEPTH; ++j)
 #pragma unroll
 			for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
-		auto accumulate = [&](const uint32_t (&w)[WPT], const float (&wt)[WS], int s) {
+		int r = rlo, y = vt.band_ys[band];
+		// One source row into the accumulator ring; slot s holds the output row that is open first.
+		auto row = [&](int s) {
 			float u[NV];
-			unpack8<DEEP>(w, u);
+			load_row(u);
+			const float *w = vt.wt + (r - vt.row_base) * WS;     // uniform address: constant bank -> uniform registers
 #pragma unroll
-			for (int j = 0; j < DEPTH; ++j)
+			for (int j = 0; j < DEPTH - 1; ++j)
 #pragma unroll
-				for (int i = 0; i < NV; ++i) acc[(s + j) % DEPTH][i] = fmaf(wt[j], u[i], acc[(s + j) % DEPTH][i]);
+				for (int i = 0; i < NV; ++i) acc[(s + j) % DEPTH][i] = fmaf(w[j], u[i], acc[(s + j) % DEPTH][i]);
+			if (w[DEPTH - 1] != 0.0f) {                          // the newest output row is touched by few rows
+#pragma unroll
+				for (int i = 0; i < NV; ++i)
+					acc[(s + DEPTH - 1) % DEPTH][i] = fmaf(w[DEPTH - 1], u[i], acc[(s + DEPTH - 1) % DEPTH][i]);
+			}
+			++r;
 		};
-		// software pipeline: row r+1 is fetched from shared memory before row r is accumulated
-		uint32_t cw[WPT], nw[WPT];
-		float cwt[WS], nwt[WS];
-		int r = rlo, y = ys;
-		fetch(cw, cwt);
 		while (y < y1) {
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					const int need = lds<int>(ytab + 4 * (y - ys));
-					while (r <= need) {
-						if (r < rhi) fetch(nw, nwt);
-						accumulate(cw, cwt, s);
-						++r;
-						if (r > need) {
-#pragma unroll
-							for (int i = 0; i < WPT; ++i) cw[i] = nw[i];
-#pragma unroll
-							for (int i = 0; i < WS; ++i) cwt[i] = nwt[i];
-							break;
-						}
-						if (r < rhi) fetch(cw, cwt);
-						accumulate(nw, nwt, s);
-						++r;
-					}
+					int n = vt.ytab[y - vt.out_base] - r + 1;        // rows still missing for output y
+					for (; n >= 2; n -= 2) { row(s); row(s); }
+					if (n > 0) row(s);
 					if (y >= y0) {
 						emit_row(gcount, acc[s]);
 						++gcount;
@@ -422,13 +406,10 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		}
 	} else {
 		float win[DEPTH][NV];
-		float unused[WS];
-		int rb = lds<int>(ytab), rnext = rb;
-		auto load_window_row = [&](float *dstv) {
+		int rb = vt.ytab[y0 - vt.out_base], rnext = rb;
+		auto load_window_row = [&](float (&dstv)[NV]) {
 			if (rnext <= rhi) {
-				uint32_t w[WPT];
-				fetch(w, unused);
-				unpack8<DEEP>(w, dstv);
+				load_row(dstv);
 				++rnext;
 			} else {
 #pragma unroll
@@ -442,19 +423,13 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					while (y < y1 && lds<int>(ytab + 4 * (y - y0)) == rb) {
-						const int wp = L.ywt + (y - y0) * wrow;
-						float w[WS];
-#pragma unroll
-						for (int q = 0; q < WS / 4; ++q) {
-							const float4 v = lds<float4>(wp + 16 * q);
-							w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-						}
+					while (y < y1 && vt.ytab[y - vt.out_base] == rb) {
+						const float *w = vt.wt + (y - vt.out_base) * WS;
 						float o[NV];
 #pragma unroll
-						for (int i = 0; i < NV; ++i) o[i] = 0.0f;
+						for (int i = 0; i < NV; ++i) o[i] = w[0] * win[s][i];
 #pragma unroll
-						for (int k = 0; k < DEPTH; ++k)
+						for (int k = 1; k < DEPTH; ++k)
 #pragma unroll
 							for (int i = 0; i < NV; ++i) o[i] = fmaf(w[k], win[(s + k) % DEPTH][i], o[i]);
 						emit_row(gcount, o);
@@ -501,28 +476,40 @@ EncodeTiledFn encode_fn() {
 	return fn;
 }
 
-template <int VARIANT, int DEPTH, bool DEEP>
-cudaError_t launch_one(const CUtensorMap &map, const DevBatch &dst, int n, const FastTables &t, int channels,
-                       int smem_bytes, cudaStream_t stream) {
+struct LaunchArgs {
+	const CUtensorMap *map;
+	const DevBatch *dst;
+	const FastTables *t;
+	const VTable *vt;
+	int n, channels, smem_bytes, bands;
+	cudaStream_t stream;
+};
+
+template <int VARIANT, int DEPTH, bool DEEP> cudaError_t launch_one(const LaunchArgs &a) {
 	auto kern = resize_fast_kernel<VARIANT, DEPTH, DEEP>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
 	if (e != cudaSuccess) return e;
-	dim3 grid((dst.width + t.tile_w - 1) / t.tile_w, (dst.height + t.band_h - 1) / t.band_h, n);
-	kern<<<grid, NT, smem_bytes, stream>>>(map, dst, t, channels);
+	dim3 grid((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
+	kern<<<grid, NT, a.smem_bytes, a.stream>>>(*a.map, *a.dst, *a.t, *a.vt, a.channels);
 	return cudaGetLastError();
 }
 
-template <int VARIANT, bool DEEP>
-cudaError_t launch_depth(const CUtensorMap &map, const DevBatch &dst, int n, const FastTables &t, int channels,
-                         int smem_bytes, cudaStream_t stream) {
-	const int d = t.depth;
-	if (d <= 3) return launch_one<VARIANT, 3, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
-	if (d <= 4) return launch_one<VARIANT, 4, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
-	if (d <= 5) return launch_one<VARIANT, 5, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
-	if (d <= 6) return launch_one<VARIANT, 6, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
-	if (d <= 8) return launch_one<VARIANT, 8, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
-	if (d <= 12) return launch_one<VARIANT, 12, DEEP>(map, dst, n, t, channels, smem_bytes, stream);
+template <int VARIANT, bool DEEP> cudaError_t launch_depth(const LaunchArgs &a) {
+	const int d = a.t->depth;
+	if (d <= 3) return launch_one<VARIANT, 3, DEEP>(a);
+	if (d <= 4) return launch_one<VARIANT, 4, DEEP>(a);
+	if (d <= 5) return launch_one<VARIANT, 5, DEEP>(a);
+	if (d <= 6) return launch_one<VARIANT, 6, DEEP>(a);
+	if (d <= 8) return launch_one<VARIANT, 8, DEEP>(a);
+	if (d <= 12) return launch_one<VARIANT, 12, DEEP>(a);
 	return cudaErrorNotSupported;
+}
+
+int padded_depth(int d) {   // DEPTH the kernel is instantiated with
+	const int steps[] = {3, 4, 5, 6, 8, 12};
+	for (int s : steps)
+		if (d <= s) return s;
+	return 0;
 }
 
 }  // namespace
@@ -546,19 +533,20 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 	return 0;
 }
 
-cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &t,
-                               cudaStream_t stream, int *launches) {
+cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &tables,
+                               const FastAxisY &fy, cudaStream_t stream, int *launches) {
 	static const int kBytes[8] = {3, 4, 1, 2, 2, 4, 6, 8}, kChannels[8] = {3, 4, 1, 2, 1, 2, 3, 4};
 	const int bpp = kBytes[src.pixel], channels = kChannels[src.pixel];
 	const bool deep = src.pixel >= 4;
-	if (t.variant < 0 || t.tile_w <= 0 || t.depth > kFastMaxDepth) return cudaErrorNotSupported;
+	FastTables t = tables;
+	const int depth = padded_depth(fy.depth);
+	if (fy.variant < 0 || t.tile_w <= 0 || depth == 0) return cudaErrorNotSupported;
 	if ((reinterpret_cast<uintptr_t>(src.base) & 15) || (src.stride & 15) || (n > 1 && (src.step & 15)))
 		return cudaErrorNotSupported;
-	if (n > 65535 || (dst.height + t.band_h - 1) / t.band_h > 65535) return cudaErrorNotSupported;
+	if (n > 65535) return cudaErrorNotSupported;
 	EncodeTiledFn encode = encode_fn();
 	if (!encode) return cudaErrorNotSupported;
-
-	const SmemLayout L = smem_layout(deep, t.tile_w, bpp, t.xstride, t.variant, t.ystride, t.band_h + kFastMaxDepth);
+	const SmemLayout L = smem_layout(deep, t.tile_w, bpp, t.xstride);
 	if (L.total > max_dynamic_smem()) return cudaErrorNotSupported;
 
 	// The batch as a 3-D tensor of 32-bit words: (words per row, rows, images).
@@ -575,12 +563,71 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
 
-	*launches += 1;
-	if (t.variant == 0)
-		return deep ? launch_depth<0, true>(map, dst, n, t, channels, L.total, stream)
-		            : launch_depth<0, false>(map, dst, n, t, channels, L.total, stream);
-	return deep ? launch_depth<1, true>(map, dst, n, t, channels, L.total, stream)
-	            : launch_depth<1, false>(map, dst, n, t, channels, L.total, stream);
+	// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, tall strips (little
+	// vertical halo) when it is large; multiples of 8 rows; small enough that one band's vertical
+	// tables fit a launch's parameter block.
+	const int WS = (depth + 3) & ~3;
+	const int dh = dst.height;
+	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
+	long long want = (148LL * 4 * 16 + tiles - 1) / tiles;
+	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
+	if (want > max_bands) want = max_bands;
+	if (want < 1) want = 1;
+	int band_h = (int)(((dh + want - 1) / want + 7) / 8 * 8);
+	auto band_fits = [&](int y0, int y1) {
+		const int rows = fy.cum[y1 - 1] - fy.smin[y0] + 1;
+		const int outs = fy.variant == 0 ? y1 - fy.ybase[fy.smin[y0]] : y1 - y0;
+		return outs <= kYtabMax && (fy.variant == 0 ? rows : outs) * WS <= kWtMax;
+	};
+	for (;;) {
+		bool ok = true;
+		for (int y0 = 0; y0 < dh && ok; y0 += band_h) ok = band_fits(y0, std::min(dh, y0 + band_h));
+		if (ok) break;
+		if (band_h <= 8) return cudaErrorNotSupported;
+		band_h = (band_h / 2 + 7) / 8 * 8;
+	}
+	t.band_h = band_h;
+	t.depth = depth;
+
+	LaunchArgs a;
+	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = L.total; a.stream = stream;
+	VTable vt;
+	a.vt = &vt;
+	// Groups of consecutive bands whose tables fit one parameter block; one launch per group.
+	for (int yb = 0; yb < dh;) {
+		int ye = yb, bands = 0;
+		while (ye < dh && bands < kMaxBands && band_fits(yb, std::min(dh, ye + band_h))) {
+			ye = std::min(dh, ye + band_h);
+			++bands;
+		}
+		if (bands == 0) return cudaErrorNotSupported;
+		vt.y_begin = yb;
+		vt.y_end = ye;
+		const int row_lo = fy.smin[yb], row_hi = fy.cum[ye - 1];
+		vt.row_base = row_lo;
+		vt.out_base = fy.variant == 0 ? fy.ybase[row_lo] : yb;
+		for (int b = 0; b < bands; ++b) {
+			const int y0 = yb + b * band_h, y1 = std::min(ye, y0 + band_h);
+			vt.band_rlo[b] = fy.smin[y0];
+			vt.band_rhi[b] = fy.cum[y1 - 1];
+			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[fy.smin[y0]] : y0;
+		}
+		const int *ysrc = fy.variant == 0 ? fy.cum.data() : fy.lo.data();
+		for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
+		// weight rows are re-strided from the host table's stride to the kernel's WS
+		const int first = fy.variant == 0 ? row_lo : yb, last = fy.variant == 0 ? row_hi : ye - 1;
+		for (int i = first; i <= last; ++i)
+			for (int j = 0; j < WS; ++j)
+				vt.wt[(i - first) * WS + j] = j < fy.stride ? fy.wv[(size_t)i * fy.stride + j] : 0.0f;
+		a.bands = bands;
+		cudaError_t e;
+		if (fy.variant == 0) e = deep ? launch_depth<0, true>(a) : launch_depth<0, false>(a);
+		else e = deep ? launch_depth<1, true>(a) : launch_depth<1, false>(a);
+		if (e != cudaSuccess) return e;
+		*launches += 1;
+		yb = ye;
+	}
+	return cudaSuccess;
 }
 
 }  // namespace picha_b200
