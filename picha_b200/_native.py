@@ -11,7 +11,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpicha_b200.so")
+# PICHA_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PICHA_B200_LIB") or os.path.join(_HERE, "libpicha_b200.so")
 
 PIXELS = ["rgb", "rgba", "grey", "greya", "r16", "r16g16", "r16g16b16", "r16g16b16a16"]
 FILTERS = ["cubic", "lanczos", "catmulrom", "mitchel", "box", "triangle"]

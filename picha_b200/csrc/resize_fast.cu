@@ -45,9 +45,20 @@ namespace {
 
 constexpr int NT = kFastThreads;
 constexpr int NV = kFastValuesPerThread;
-constexpr int RS = 8;              // source rows per TMA stage
-constexpr int NS = 3;              // stages in the ring
-constexpr int G = 8;               // output rows per pass-2 group
+#ifndef PICHA_FAST_RS
+#define PICHA_FAST_RS 8
+#endif
+#ifndef PICHA_FAST_NS
+#define PICHA_FAST_NS 3
+#endif
+#ifndef PICHA_FAST_G
+#define PICHA_FAST_G 8
+#endif
+constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage
+constexpr int NS = PICHA_FAST_NS;  // stages in the ring
+constexpr int G = PICHA_FAST_G;    // output rows per pass-2 group (4 or 8)
+constexpr int RPT = G / 4;         // output rows a pass-2 thread produces (they share the x weights)
+static_assert(G == 4 || G == 8, "pass 2 maps 4 rows to the low lane bits");
 constexpr int TMPS = NT * NV + 4;  // floats per intermediate row (+4: rows land 4 banks apart)
 
 // Vertical tables of one launch, passed by value as a __grid_constant__ kernel parameter (the
@@ -193,7 +204,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 	for (int o = a.tid; o < a.tw * 4; o += NT) {
 		const int g = o & 3, xx = o >> 2;
 		if (g >= a.ng) continue;
-		const bool two = g + 4 < a.ng;
+		const bool two = RPT == 2 && g + 4 < a.ng;
 		const int cnt = lds<int>(a.xc + 4 * xx);
 		const int w = a.xw + 4 * xx * a.xstride;
 		const int v0 = a.tmp + 4 * (g * TMPS + lds<int>(a.xf + 4 * xx) * C);
@@ -327,20 +338,33 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		rows_left = RS;
 		doff = L.ring + slot * RS * L.row_bytes + thread_byte;
 	};
-	auto load_row = [&](float (&u)[NV]) {
-		if (rows_left == 0) next_stage();
-		--rows_left;
-		uint32_t w[WPT];
-		if (DEEP) {
-			const uint4 v = lds<uint4>(doff);
-			w[0] = v.x; w[1] = v.y; w[2 % WPT] = v.z; w[3 % WPT] = v.w;
-		} else {
-			const uint2 v = lds<uint2>(doff);
-			w[0] = v.x; w[1] = v.y;
+	// The words of row i+1 are read from shared memory while row i is being accumulated, so the
+	// LDS latency is covered by this warp's own FMAs rather than by other warps.
+	uint32_t pw[WPT];
+	int rows_to_fetch = rhi - rlo + 1;              // uniform
+	auto prefetch = [&]() {
+		if (rows_to_fetch > 0) {
+			--rows_to_fetch;
+			if (rows_left == 0) next_stage();
+			--rows_left;
+			if (DEEP) {
+				const uint4 v = lds<uint4>(doff);
+				pw[0] = v.x; pw[1] = v.y; pw[2 % WPT] = v.z; pw[3 % WPT] = v.w;
+			} else {
+				const uint2 v = lds<uint2>(doff);
+				pw[0] = v.x; pw[1] = v.y;
+			}
+			doff += 1024;
 		}
-		doff += 1024;
+	};
+	auto load_row = [&](float (&u)[NV]) {
+		uint32_t w[WPT];
+#pragma unroll
+		for (int i = 0; i < WPT; ++i) w[i] = pw[i];
+		prefetch();
 		unpack8<DEEP>(w, u);
 	};
+	prefetch();
 
 	Pass2Args pa;
 	pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
