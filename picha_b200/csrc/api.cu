@@ -304,9 +304,6 @@ int check_convert(const picha_b200_image *s, const picha_b200_image *d) {
 	return 0;
 }
 
-bool same_shape(const picha_b200_image &a, const picha_b200_image &b) {
-	return a.width == b.width && a.height == b.height && a.pixel == b.pixel;
-}
 
 // ---- host <-> device staging ---------------------------------------------------------------
 

@@ -23,14 +23,21 @@ template <> struct Depth<true> {
 	static constexpr float inv = 1 / 65535.0f;
 };
 
+// Both directions avoid the I2F / F2I conversion instructions, which issue at a quarter of the FP32
+// rate on this part and would bound the luma conversions (tools/microbench/unpack_issue.cu):
+//   unpack  0x4B000000 | v is the float 2^23 + v; fma(2^23 + v, inv, -2^23 * inv) forms the exact
+//           product v * inv and rounds it once -- bit-identical to float(v) * inv;
+//   pack    after the clamp t is in [0, max] so the truncating cast is floor(t): adding 2^23 with
+//           round-toward-minus-infinity leaves floor(t) in the low mantissa bits.
 template <bool DEEP> __device__ __forceinline__ float unpack_value(unsigned v) {
-	return __fmul_rn(__uint2float_rn(v), Depth<DEEP>::inv);
+	return __fmaf_rn(__uint_as_float(0x4B000000u | v), Depth<DEEP>::inv, -8388608.0f * Depth<DEEP>::inv);
 }
 
 template <bool DEEP> __device__ __forceinline__ unsigned pack_value(float f) {
-	float t = __fadd_rn(__fadd_rn(0.0f, __fmul_rn(f, Depth<DEEP>::maxv)), 0.5f);
-	t = fmaxf(0.0f, fminf(Depth<DEEP>::maxv, t));
-	return (unsigned)t;   // cvt.rzi: truncation, like the C++ cast
+	// (the reference's leading "0 +" only turns -0 into +0, which the clamp and floor do as well)
+	float t = __fadd_rn(__fmul_rn(f, Depth<DEEP>::maxv), 0.5f);
+	t = fmaxf(0.0f, fminf(Depth<DEEP>::maxv, t));   // NaN -> max, like std::min/std::max in the reference
+	return __float_as_uint(__fadd_rd(t, 8388608.0f)) & 0x7FFFFFu;
 }
 
 // Unaligned-safe channel load/store (subView bases are arbitrary byte offsets).

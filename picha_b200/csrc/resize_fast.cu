@@ -54,6 +54,9 @@ constexpr int NV = kFastValuesPerThread;
 #ifndef PICHA_FAST_G
 #define PICHA_FAST_G 8
 #endif
+#ifndef PICHA_FAST_PREFETCH
+#define PICHA_FAST_PREFETCH 1
+#endif
 constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage
 constexpr int NS = PICHA_FAST_NS;  // stages in the ring
 constexpr int G = PICHA_FAST_G;    // output rows per pass-2 group (4 or 8)
@@ -358,13 +361,18 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		}
 	};
 	auto load_row = [&](float (&u)[NV]) {
-		uint32_t w[WPT];
+		if (PICHA_FAST_PREFETCH) {
+			uint32_t w[WPT];
 #pragma unroll
-		for (int i = 0; i < WPT; ++i) w[i] = pw[i];
-		prefetch();
-		unpack8<DEEP>(w, u);
+			for (int i = 0; i < WPT; ++i) w[i] = pw[i];
+			prefetch();
+			unpack8<DEEP>(w, u);
+		} else {
+			prefetch();
+			unpack8<DEEP>(pw, u);
+		}
 	};
-	prefetch();
+	if (PICHA_FAST_PREFETCH) prefetch();
 
 	Pass2Args pa;
 	pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
