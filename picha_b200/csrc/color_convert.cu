@@ -124,7 +124,7 @@ __device__ __forceinline__ void convert_one_unaligned(const uint8_t *s, uint8_t 
 
 template <int SC, bool SDEEP, int DC, bool DDEEP>
 __global__ void __launch_bounds__(kWarps * 32)
-convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, long long total_groups, float rf, float gf, float bf) {
+convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, float gf, float bf) {
 	constexpr int SW = SC * Depth<SDEEP>::bytes;   // source words per lane per step (= bytes per pixel)
 	constexpr int DW = DC * Depth<DDEEP>::bytes;
 	__shared__ __align__(16) unsigned tile_in[kWarps][SW * 32];
@@ -132,22 +132,31 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, long long to
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned *tin = tile_in[warp], *tout = tile_out[warp];
-	const long long groups_per_image = (long long)groups_per_row * src.height;
+	// A warp owns one 128-pixel column group and walks down the rows (no per-step index division;
+	// only warp-level synchronisation is used, so a warp without a group simply leaves).
+	const int gx = blockIdx.x * kWarps + warp;
+	if (gx >= groups_per_row) return;
+	const int px0 = gx * kGroup;
+	const int npx = min(kGroup, src.width - px0);
+	const uint8_t *simg = src.base + (long long)blockIdx.z * src.step + (long long)px0 * SW;
+	uint8_t *dimg = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * DW;
 
-	for (long long g = (long long)blockIdx.x * kWarps + warp; g < total_groups; g += (long long)gridDim.x * kWarps) {
-		const long long img = g / groups_per_image;
-		const int rem = (int)(g - img * groups_per_image);
-		const int y = rem / groups_per_row, gx = rem - y * groups_per_row;
-		const int px0 = gx * kGroup;
-		const uint8_t *srow = src.base + img * src.step + (long long)y * src.stride + (long long)px0 * SW;
-		uint8_t *drow = dst.base + img * dst.step + (long long)y * dst.stride + (long long)px0 * DW;
-		const int npx = min(kGroup, src.width - px0);
-
-		if (npx == kGroup) {
-			const unsigned *s32 = reinterpret_cast<const unsigned *>(srow);
-			unsigned win[SW];
+	if (npx == kGroup) {
+		// full group: 32-bit coalesced loads, one row ahead of the row being converted
+		unsigned win[SW];
+		int y = blockIdx.y;
+		if (y < src.height) {
+			const unsigned *s32 = reinterpret_cast<const unsigned *>(simg + (long long)y * src.stride);
 #pragma unroll
 			for (int j = 0; j < SW; ++j) win[j] = __ldg(s32 + j * 32 + lane);
+		}
+		for (; y < src.height; y += gridDim.y) {
+			unsigned nxt[SW];
+			if (y + (int)gridDim.y < src.height) {
+				const unsigned *s32 = reinterpret_cast<const unsigned *>(simg + (long long)(y + gridDim.y) * src.stride);
+#pragma unroll
+				for (int j = 0; j < SW; ++j) nxt[j] = __ldg(s32 + j * 32 + lane);
+			}
 			__syncwarp();   // previous step's readers are done with the tiles
 #pragma unroll
 			for (int j = 0; j < SW; ++j) tin[j * 32 + lane] = win[j];
@@ -169,11 +178,17 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, long long to
 			}
 			lane_words_store<DW>(tout, packed, lane);
 			__syncwarp();
-			unsigned *d32 = reinterpret_cast<unsigned *>(drow);
+			unsigned *d32 = reinterpret_cast<unsigned *>(dimg + (long long)y * dst.stride);
 #pragma unroll
 			for (int j = 0; j < DW; ++j) d32[j * 32 + lane] = tout[j * 32 + lane];
-		} else {
-			// row tail: fewer than 128 pixels left; only payload bytes may be written
+#pragma unroll
+			for (int j = 0; j < SW; ++j) win[j] = nxt[j];
+		}
+	} else {
+		// row tail: fewer than 128 pixels left; only payload bytes may be written
+		for (int y = blockIdx.y; y < src.height; y += gridDim.y) {
+			const uint8_t *srow = simg + (long long)y * src.stride;
+			uint8_t *drow = dimg + (long long)y * dst.stride;
 			for (int p = lane; p < npx; p += 32)
 				convert_one_unaligned<SC, SDEEP, DC, DDEEP>(srow + p * SW, drow + p * DW, rf, gf, bf);
 		}
@@ -232,14 +247,20 @@ cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float r
                         cudaStream_t stream, int *launches) {
 	if (aligned4(src) && aligned4(dst)) {
 		const int gpr = (src.width + kGroup - 1) / kGroup;
-		const long long total = (long long)gpr * src.height * n;
-		// persistent-style grid: a multiple of the SM count, capped by the work available
-		long long want = (total + kWarps - 1) / kWarps;
-		long long cap = (long long)sm_count() * 16;
-		int grid = (int)(want < cap ? want : cap);
-		if (grid < 1) grid = 1;
-		convert_rows_kernel<SC, SDEEP, DC, DDEEP><<<grid, kWarps * 32, 0, stream>>>(src, dst, gpr, total, rf, gf, bf);
-		*launches += 1;
+		const int gx = (gpr + kWarps - 1) / kWarps;
+		for (int z0 = 0; z0 < n; z0 += 65535) {
+			const int nz = n - z0 < 65535 ? n - z0 : 65535;
+			// rows are dealt out over gridDim.y so that the grid is about 32 CTAs per SM in total
+			long long gy = ((long long)sm_count() * 32 + (long long)gx * nz - 1) / ((long long)gx * nz);
+			if (gy > src.height) gy = src.height;
+			if (gy > 65535) gy = 65535;
+			if (gy < 1) gy = 1;
+			DevBatch s = src, d = dst;
+			s.base += (long long)z0 * src.step;
+			d.base += (long long)z0 * dst.step;
+			convert_rows_kernel<SC, SDEEP, DC, DDEEP><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
+			*launches += 1;
+		}
 		return cudaGetLastError();
 	}
 	for (int z0 = 0; z0 < n; z0 += 65535) {
