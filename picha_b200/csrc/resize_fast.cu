@@ -54,9 +54,7 @@ constexpr int NV = kFastValuesPerThread;
 #ifndef PICHA_FAST_G
 #define PICHA_FAST_G 8
 #endif
-#ifndef PICHA_FAST_PREFETCH
-#define PICHA_FAST_PREFETCH 1
-#endif
+
 constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage
 constexpr int NS = PICHA_FAST_NS;  // stages in the ring
 constexpr int G = PICHA_FAST_G;    // output rows per pass-2 group (4 or 8)
@@ -145,22 +143,23 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // ---- unpack: exact float(v) * (1/max) in one FMA ----------------------------------------------
 // 0x4B000000 | v is the float 2^23 + v; fma(2^23 + v, inv, -2^23*inv) rounds the exact product
 // v*inv once, which is the reference's float(v) * inv (src/picha.h:98-105).
-template <bool DEEP> __device__ __forceinline__ void unpack8(const uint32_t *w, float *u) {
-	constexpr float inv = Depth<DEEP>::inv;
-	constexpr float bias = -8388608.0f * inv;
+// `magic` (0x4B000000) and `inv` are passed in as registers the caller made opaque to the compiler:
+// as literals they are rematerialised with two extra instructions in every row body.
+template <bool DEEP> __device__ __forceinline__ void unpack8(const uint32_t *w, float *u, uint32_t magic, float inv) {
+	constexpr float bias = -8388608.0f * Depth<DEEP>::inv;
 	if (DEEP) {
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			u[2 * i] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7410)), inv, bias);
-			u[2 * i + 1] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7432)), inv, bias);
+			u[2 * i] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7410)), inv, bias);
+			u[2 * i + 1] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7432)), inv, bias);
 		}
 	} else {
 #pragma unroll
 		for (int i = 0; i < 2; ++i) {
-			u[4 * i + 0] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7440)), inv, bias);
-			u[4 * i + 1] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7441)), inv, bias);
-			u[4 * i + 2] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7442)), inv, bias);
-			u[4 * i + 3] = fmaf(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7443)), inv, bias);
+			u[4 * i + 0] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7440)), inv, bias);
+			u[4 * i + 1] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7441)), inv, bias);
+			u[4 * i + 2] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7442)), inv, bias);
+			u[4 * i + 3] = fmaf(__uint_as_float(__byte_perm(w[i], magic, 0x7443)), inv, bias);
 		}
 	}
 }
@@ -341,38 +340,28 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		rows_left = RS;
 		doff = L.ring + slot * RS * L.row_bytes + thread_byte;
 	};
-	// The words of row i+1 are read from shared memory while row i is being accumulated, so the
-	// LDS latency is covered by this warp's own FMAs rather than by other warps.
-	uint32_t pw[WPT];
-	int rows_to_fetch = rhi - rlo + 1;              // uniform
-	auto prefetch = [&]() {
-		if (rows_to_fetch > 0) {
-			--rows_to_fetch;
-			if (rows_left == 0) next_stage();
-			--rows_left;
-			if (DEEP) {
-				const uint4 v = lds<uint4>(doff);
-				pw[0] = v.x; pw[1] = v.y; pw[2 % WPT] = v.z; pw[3 % WPT] = v.w;
-			} else {
-				const uint2 v = lds<uint2>(doff);
-				pw[0] = v.x; pw[1] = v.y;
-			}
-			doff += 1024;
+	// Next row of the tile for this thread.  Called one row ahead of the row being accumulated, so
+	// the LDS latency is covered by this warp's own FMAs.  Past the band's last stage it does
+	// nothing; inside the last stage it may read rows beyond rhi (staged, never used).
+	auto fetch = [&](uint32_t (&w)[WPT]) {
+		if (rows_left == 0) {
+			if (stage + 1 >= nstages) return;
+			next_stage();
 		}
-	};
-	auto load_row = [&](float (&u)[NV]) {
-		if (PICHA_FAST_PREFETCH) {
-			uint32_t w[WPT];
-#pragma unroll
-			for (int i = 0; i < WPT; ++i) w[i] = pw[i];
-			prefetch();
-			unpack8<DEEP>(w, u);
+		--rows_left;
+		if (DEEP) {
+			const uint4 v = lds<uint4>(doff);
+			w[0] = v.x; w[1] = v.y; w[2 % WPT] = v.z; w[3 % WPT] = v.w;
 		} else {
-			prefetch();
-			unpack8<DEEP>(pw, u);
+			const uint2 v = lds<uint2>(doff);
+			w[0] = v.x; w[1] = v.y;
 		}
+		doff += 1024;
 	};
-	if (PICHA_FAST_PREFETCH) prefetch();
+	uint32_t magic;
+	float inv;
+	asm volatile("mov.b32 %0, 0x4B000000;" : "=r"(magic));
+	asm volatile("mov.f32 %0, %1;" : "=f"(inv) : "f"(Depth<DEEP>::inv));
 
 	Pass2Args pa;
 	pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
@@ -399,11 +388,14 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 #pragma unroll
 			for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
 		int r = rlo, y = vt.band_ys[band];
+		int widx = (rlo - vt.row_base) * WS;                     // uniform index of row r's weights
 		// One source row into the accumulator ring; slot s holds the output row that is open first.
-		auto row = [&](int s) {
+		// `cur` holds row r's words, row r+1 is fetched into `nxt` meanwhile.
+		auto row = [&](int s, const uint32_t (&cur)[WPT], uint32_t (&nxt)[WPT]) {
+			fetch(nxt);
 			float u[NV];
-			load_row(u);
-			const float *w = vt.wt + (r - vt.row_base) * WS;     // uniform address: constant bank -> uniform registers
+			unpack8<DEEP>(cur, u, magic, inv);
+			const float *w = vt.wt + widx;                       // constant bank -> uniform registers
 #pragma unroll
 			for (int j = 0; j < DEPTH - 1; ++j)
 #pragma unroll
@@ -413,15 +405,23 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 				for (int i = 0; i < NV; ++i)
 					acc[(s + DEPTH - 1) % DEPTH][i] = fmaf(w[DEPTH - 1], u[i], acc[(s + DEPTH - 1) % DEPTH][i]);
 			}
-			++r;
+			widx += WS;
 		};
+		uint32_t wa[WPT], wb[WPT];
+		fetch(wa);
 		while (y < y1) {
 #pragma unroll
 			for (int s = 0; s < DEPTH; ++s) {
 				if (y < y1) {
-					int n = vt.ytab[y - vt.out_base] - r + 1;        // rows still missing for output y
-					for (; n >= 2; n -= 2) { row(s); row(s); }
-					if (n > 0) row(s);
+					const int need = vt.ytab[y - vt.out_base];       // output y is complete after this row
+					int n = need - r + 1;
+					r = need + 1;
+					for (; n >= 2; n -= 2) { row(s, wa, wb); row(s, wb, wa); }
+					if (n > 0) {
+						row(s, wa, wb);
+#pragma unroll
+						for (int i = 0; i < WPT; ++i) wa[i] = wb[i];
+					}
 					if (y >= y0) {
 						emit_row(gcount, acc[s]);
 						++gcount;
@@ -439,9 +439,15 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	} else {
 		float win[DEPTH][NV];
 		int rb = vt.ytab[y0 - vt.out_base], rnext = rb;
+		uint32_t pw[WPT];
+		fetch(pw);
 		auto load_window_row = [&](float (&dstv)[NV]) {
 			if (rnext <= rhi) {
-				load_row(dstv);
+				uint32_t w[WPT];
+#pragma unroll
+				for (int i = 0; i < WPT; ++i) w[i] = pw[i];
+				fetch(pw);
+				unpack8<DEEP>(w, dstv, magic, inv);
 				++rnext;
 			} else {
 #pragma unroll
