@@ -102,13 +102,44 @@ __host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp
 
 extern __shared__ __align__(128) uint8_t smem[];
 
-// Shared-memory locations travel as byte offsets into the CTA's dynamic shared memory so that every
-// access stays an LDS/STS with 32-bit addressing.
-template <typename T> __device__ __forceinline__ T lds(int byte_offset) {
-	return *reinterpret_cast<const T *>(smem + byte_offset);
+// Shared-memory locations travel as 32-bit shared-window addresses (base of the CTA's dynamic
+// shared memory + byte offset) and are accessed with explicit ld.shared / st.shared: through C++
+// pointers the compiler re-derives the window base from SR_CgaCtaId (an S2UR with scoreboard
+// latency) in front of every access of the row loop.
+template <typename T> __device__ __forceinline__ T lds(uint32_t addr);
+template <> __device__ __forceinline__ uint4 lds<uint4>(uint32_t addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+	return v;
 }
-template <typename T> __device__ __forceinline__ void sts(int byte_offset, const T &v) {
-	*reinterpret_cast<T *>(smem + byte_offset) = v;
+template <> __device__ __forceinline__ uint2 lds<uint2>(uint32_t addr) {
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+	return v;
+}
+template <> __device__ __forceinline__ float4 lds<float4>(uint32_t addr) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+template <> __device__ __forceinline__ float lds<float>(uint32_t addr) {
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+	return v;
+}
+template <> __device__ __forceinline__ int lds<int>(uint32_t addr) {
+	int v;
+	asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts(uint32_t addr, const float4 &v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts(uint32_t addr, float v) {
+	asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts(uint32_t addr, int v) {
+	asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -192,6 +223,7 @@ template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint8_t 
 // Lanes: g fastest (4 rows), then 8 different xx per warp -- float4 reads of a quarter-warp fall in
 // distinct banks (rows are 4 banks apart, neighbouring columns of a 4:1 downscale 16 banks apart).
 struct Pass2Args {
+	uint32_t sbase;        // shared-window address of the CTA's dynamic shared memory
 	int tmp;               // float [G][TMPS]
 	int xw;                // float [tile_w][xstride], zero padded
 	int xf, xc;            // int: first source pixel (relative to the tile origin), taps
@@ -207,10 +239,10 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		const int g = o & 3, xx = o >> 2;
 		if (g >= a.ng) continue;
 		const bool two = RPT == 2 && g + 4 < a.ng;
-		const int cnt = lds<int>(a.xc + 4 * xx);
-		const int w = a.xw + 4 * xx * a.xstride;
-		const int v0 = a.tmp + 4 * (g * TMPS + lds<int>(a.xf + 4 * xx) * C);
-		const int v1 = v0 + (two ? 16 * TMPS : 0);
+		const int cnt = lds<int>(a.sbase + a.xc + 4 * xx);
+		const uint32_t w = a.sbase + a.xw + 4 * xx * a.xstride;
+		const uint32_t v0 = a.sbase + a.tmp + 4 * (g * TMPS + lds<int>(a.sbase + a.xf + 4 * xx) * C);
+		const uint32_t v1 = v0 + (two ? 16 * TMPS : 0);
 		float acc0[C], acc1[C];
 #pragma unroll
 		for (int ch = 0; ch < C; ++ch) acc0[ch] = acc1[ch] = 0.0f;
@@ -261,7 +293,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 	const int nvec = vec ? row_bytes >> 4 : 0;
 	for (int i = a.tid; i < a.ng * nvec; i += NT) {
 		const int g = i / nvec, j = i - g * nvec;
-		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.outt + g * a.out_stride + 16 * j);
+		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
 	}
 	const int tail0 = nvec << 4, tail = row_bytes - tail0;
 	for (int i = a.tid; i < a.ng * tail; i += NT) {
@@ -302,6 +334,8 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 
 	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
+	uint32_t sbase = smem_u32(smem);
+	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
 
 	auto issue_stage = [&](int k) {
 		constexpr int BOXES = DEEP ? 2 : 1;      // TMA boxes are at most 256 elements wide
@@ -319,17 +353,17 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		for (int k = 0; k < NS - 1 && k < nstages; ++k) issue_stage(k);
 	}
 	// this tile's horizontal tables -> shared memory
-	for (int i = tid; i < tw * t.xstride; i += NT) sts(L.xw + 4 * i, t.xw[(long long)x0 * t.xstride + i]);
+	for (int i = tid; i < tw * t.xstride; i += NT) sts(sbase + L.xw + 4 * i, t.xw[(long long)x0 * t.xstride + i]);
 	for (int i = tid; i < tw; i += NT) {
-		sts(L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
-		sts(L.xc + 4 * i, t.xcount[x0 + i]);
+		sts(sbase + L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
+		sts(sbase + L.xc + 4 * i, t.xcount[x0 + i]);
 	}
 	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
 	// ---- ring consumer -------------------------------------------------------------------------
 	int stage = -1, slot = NS - 1, rows_left = 0;   // uniform
 	uint32_t parity = 1;
-	int doff = 0;                                   // byte offset of this thread's words in the next row
+	uint32_t doff = 0;                              // shared address of this thread's words in the next row
 	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255));
 	auto next_stage = [&]() {
 		__syncthreads();                  // every thread has finished the previous stage
@@ -338,7 +372,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
 		mbar_wait(bars + slot, parity);
 		rows_left = RS;
-		doff = L.ring + slot * RS * L.row_bytes + thread_byte;
+		doff = sbase + L.ring + slot * RS * L.row_bytes + thread_byte;
 	};
 	// Next row of the tile for this thread.  Called one row ahead of the row being accumulated, so
 	// the LDS latency is covered by this warp's own FMAs.  Past the band's last stage it does
@@ -364,13 +398,13 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	asm volatile("mov.f32 %0, %1;" : "=f"(inv) : "f"(Depth<DEEP>::inv));
 
 	Pass2Args pa;
-	pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
+	pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
 	pa.xstride = t.xstride; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid;
 	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * bpp;
-	const int my_tmp = L.tmp + tid * NV * 4;
+	const uint32_t my_tmp = sbase + L.tmp + tid * NV * 4;
 
 	auto emit_row = [&](int g, const float *v) {
-		const int d = my_tmp + g * TMPS * 4;
+		const uint32_t d = my_tmp + g * TMPS * 4;
 		sts(d, make_float4(v[0], v[1], v[2], v[3]));
 		sts(d + 16, make_float4(v[4], v[5], v[6], v[7]));
 	};
