@@ -49,10 +49,10 @@ constexpr int NV = kFastValuesPerThread;
 #define PICHA_FAST_RS 8
 #endif
 #ifndef PICHA_FAST_NS
-#define PICHA_FAST_NS 3
+#define PICHA_FAST_NS 2
 #endif
 #ifndef PICHA_FAST_G
-#define PICHA_FAST_G 8
+#define PICHA_FAST_G 4
 #endif
 
 constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage
