@@ -243,7 +243,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		const PixelInfo pi = pixel_info(px);
 		const int unit = align_pixels(pi.bytes);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
-			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 256);
+			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 512);
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
@@ -258,6 +258,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->t.max_band_rows = max_rows;
 	p->ft.xfirst = ib + o_xfirst; p->ft.xcount = ib + o_xcount;
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
+	p->ft.xshort = fx.taps <= 4 ? 4 : (fx.taps <= 8 ? 8 : 0);
 
 	dev->plans[key] = p;
 	dev->lru.push_front(key);

@@ -44,6 +44,7 @@ struct FastTables {
 	const int *xfirst, *xcount;
 	const float *xw;
 	int xstride;
+	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA
 	int align_px; // tile source origins are multiples of this many pixels (16-byte TMA start)

@@ -90,7 +90,7 @@ __host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp
 	L.row_bytes = NT * NV * (deep ? 2 : 1);
 	L.ring = 0;
 	L.tmp = L.ring + NS * RS * L.row_bytes;
-	L.out = L.tmp + G * TMPS * 4;
+	L.out = L.tmp + G * TMPS * 4 + 256;   // 64 zeroed floats: padded taps of the last row may read past it
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + G * L.out_stride;
 	L.xf = L.xw + tile_w * xstride * 4;
@@ -120,6 +120,11 @@ template <> __device__ __forceinline__ uint2 lds<uint2>(uint32_t addr) {
 template <> __device__ __forceinline__ float4 lds<float4>(uint32_t addr) {
 	float4 v;
 	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+template <> __device__ __forceinline__ float2 lds<float2>(uint32_t addr) {
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
 	return v;
 }
 template <> __device__ __forceinline__ float lds<float>(uint32_t addr) {
@@ -235,7 +240,25 @@ struct Pass2Args {
 	int outt;              // bytes [G][out_stride]
 	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
 	int xstride, out_stride, dstride, tw, ng, tid;
+	int xshort;            // 4 or 8: every column has at most that many taps (unrolled path); else 0
 };
+
+// shared-memory tile -> global, 16 bytes per thread where the destination allows it
+template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) {
+	__syncthreads();
+	const int row_bytes = a.tw * BPP;
+	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
+	const int nvec = vec ? row_bytes >> 4 : 0;
+	for (int i = a.tid; i < a.ng * nvec; i += NT) {
+		const int g = i / nvec, j = i - g * nvec;
+		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
+	}
+	const int tail0 = nvec << 4, tail = row_bytes - tail0;
+	for (int i = a.tid; i < a.ng * tail; i += NT) {
+		const int g = i / tail, j = tail0 + (i - g * tail);
+		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
+	}
+}
 
 template <int C, bool DEEP>
 __device__ __noinline__ void pass2(Pass2Args a) {
@@ -290,36 +313,69 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		store_pixel<C, DEEP>(d, acc0);
 		if (two) store_pixel<C, DEEP>(d + 4 * a.out_stride, acc1);
 	}
-	__syncthreads();
+	copy_out<C * Depth<DEEP>::bytes>(a);
+}
 
-	// shared-memory tile -> global, 16 bytes per thread where the destination allows it
-	const int row_bytes = a.tw * BPP;
-	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
-	const int nvec = vec ? row_bytes >> 4 : 0;
-	for (int i = a.tid; i < a.ng * nvec; i += NT) {
-		const int g = i / nvec, j = i - g * nvec;
-		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
+// Few taps per output (upscaling): everything unrolled, weights zero-padded to XT taps, so the
+// per-pixel loop and address overhead of the general path does not dominate the 4 x C FMAs per tap.
+template <int C, bool DEEP, int XT>
+__device__ __noinline__ void pass2_short(Pass2Args a) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	for (int o = a.tid; o < a.tw * 4; o += NT) {
+		const int g = o & 3, xx = o >> 2;
+		if (g >= a.ng) continue;
+		const uint32_t w = a.sbase + a.xw + 4 * xx * a.xstride;
+		const uint32_t v0 = a.sbase + a.tmp + 4 * (g * TMPS + lds<int>(a.sbase + a.xf + 4 * xx) * C);
+		float wk[XT];
+#pragma unroll
+		for (int q = 0; q < XT / 4; ++q) {
+			const float4 wq = lds<float4>(w + 16 * q);
+			wk[4 * q] = wq.x; wk[4 * q + 1] = wq.y; wk[4 * q + 2] = wq.z; wk[4 * q + 3] = wq.w;
+		}
+		float acc[C];
+#pragma unroll
+		for (int ch = 0; ch < C; ++ch) acc[ch] = 0.0f;
+#pragma unroll
+		for (int k = 0; k < XT; ++k) {
+			if (C == 4) {
+				const float4 p = lds<float4>(v0 + 16 * k);
+				acc[0] = fmaf(wk[k], p.x, acc[0]); acc[1 % C] = fmaf(wk[k], p.y, acc[1 % C]);
+				acc[2 % C] = fmaf(wk[k], p.z, acc[2 % C]); acc[3 % C] = fmaf(wk[k], p.w, acc[3 % C]);
+			} else if (C == 2) {
+				const float2 p = lds<float2>(v0 + 8 * k);
+				acc[0] = fmaf(wk[k], p.x, acc[0]); acc[1 % C] = fmaf(wk[k], p.y, acc[1 % C]);
+			} else {
+#pragma unroll
+				for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(wk[k], lds<float>(v0 + 4 * (C * k + ch)), acc[ch]);
+			}
+		}
+		store_pixel<C, DEEP>(smem + a.outt + g * a.out_stride + xx * BPP, acc);
 	}
-	const int tail0 = nvec << 4, tail = row_bytes - tail0;
-	for (int i = a.tid; i < a.ng * tail; i += NT) {
-		const int g = i / tail, j = tail0 + (i - g * tail);
-		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
-	}
+	copy_out<BPP>(a);
+}
+
+template <int C, bool DEEP> __device__ __forceinline__ void pass2_any(const Pass2Args &a) {
+	if (a.xshort == 4) pass2_short<C, DEEP, 4>(a);
+	else if (a.xshort == 8) pass2_short<C, DEEP, 8>(a);
+	else pass2<C, DEEP>(a);
 }
 
 template <bool DEEP> __device__ __forceinline__ void run_pass2(const Pass2Args &a, int channels) {
 	__syncthreads();           // the group's intermediate rows are complete
 	switch (channels) {
-		case 1: pass2<1, DEEP>(a); break;
-		case 2: pass2<2, DEEP>(a); break;
-		case 3: pass2<3, DEEP>(a); break;
-		default: pass2<4, DEEP>(a); break;
+		case 1: pass2_any<1, DEEP>(a); break;
+		case 2: pass2_any<2, DEEP>(a); break;
+		case 3: pass2_any<3, DEEP>(a); break;
+		default: pass2_any<4, DEEP>(a); break;
 	}
 	__syncthreads();           // pass 1 may overwrite the intermediate rows again
 }
 
+#ifndef PICHA_FAST_MIN_CTAS
+#define PICHA_FAST_MIN_CTAS 1
+#endif
 template <int VARIANT, int DEPTH, bool DEEP>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (DEPTH <= 6 ? PICHA_FAST_MIN_CTAS : 1))
 resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, int channels) {
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
@@ -363,6 +419,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		sts(sbase + L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
 		sts(sbase + L.xc + 4 * i, t.xcount[x0 + i]);
 	}
+	if (tid < 64) sts(sbase + L.tmp + G * TMPS * 4 + 4 * tid, 0.0f);
 	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
 	// ---- ring consumer -------------------------------------------------------------------------
@@ -404,6 +461,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 
 	Pass2Args pa;
 	pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.xc = L.xc; pa.outt = L.out;
+	pa.xshort = t.xshort;
 	pa.xstride = t.xstride; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid;
 	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * bpp;
 	const uint32_t my_tmp = sbase + L.tmp + tid * NV * 4;
