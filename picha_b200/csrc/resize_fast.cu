@@ -372,7 +372,7 @@ template <bool DEEP> __device__ __forceinline__ void run_pass2(const Pass2Args &
 }
 
 #ifndef PICHA_FAST_MIN_CTAS
-#define PICHA_FAST_MIN_CTAS 1
+#define PICHA_FAST_MIN_CTAS 4
 #endif
 template <int VARIANT, int DEPTH, bool DEEP>
 __global__ void __launch_bounds__(NT, (DEPTH <= 6 ? PICHA_FAST_MIN_CTAS : 1))
