@@ -1,0 +1,8 @@
+// Instantiation unit of the fast resize kernels: see resize_fast.cuh / resize_fast.cu.
+#include "resize_fast.cuh"
+
+namespace picha_b200 {
+
+cudaError_t launch_fast_up_u16(const FastLaunch &a) { return fast::launch_depth<1, true>(a); }
+
+}  // namespace picha_b200
