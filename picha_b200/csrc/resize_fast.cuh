@@ -345,7 +345,7 @@ template <bool DEEP, int XS> __device__ __forceinline__ void run_pass2(const Pas
 #define PICHA_FAST_MIN_CTAS 4
 #endif
 template <int VARIANT, int DEPTH, bool DEEP, int XS>
-__global__ void __launch_bounds__(NT, (DEPTH <= 4 ? PICHA_FAST_MIN_CTAS + 1 : DEPTH <= 6 ? PICHA_FAST_MIN_CTAS : 1))
+__global__ void __launch_bounds__(NT, (VARIANT == 0 && DEPTH <= 4 ? PICHA_FAST_MIN_CTAS + 1 : DEPTH <= 6 ? PICHA_FAST_MIN_CTAS : 1))
 resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, int channels) {
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
