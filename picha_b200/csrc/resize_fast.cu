@@ -113,7 +113,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	cuuint64_t dims[3] = {row_words, (cuuint64_t)src.height, (cuuint64_t)n};
 	cuuint64_t strides[2] = {(cuuint64_t)src.stride, (cuuint64_t)(n > 1 ? src.step : (int64_t)src.stride * src.height)};
 	if (strides[1] & 15) strides[1] = (strides[1] + 15) & ~15ull;   // n == 1: never dereferenced
-	cuuint32_t box[3] = {256, RS, 1};
+	cuuint32_t box[3] = {256, (cuuint32_t)stage_rows(deep), 1};
 	cuuint32_t estr[3] = {1, 1, 1};
 	CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.base, dims, strides, box, estr,
 	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -23,7 +23,7 @@ constexpr int NV = kFastValuesPerThread;
 #define PICHA_FAST_G 4
 #endif
 
-constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage
+constexpr int RS = PICHA_FAST_RS;  // source rows per TMA stage (u8; 16-bit rows are twice as long: half as many)
 constexpr int NS = PICHA_FAST_NS;  // stages in the ring
 constexpr int G = PICHA_FAST_G;    // output rows per pass-2 group (4 or 8)
 constexpr int RPT = G / 4;         // output rows a pass-2 thread produces (they share the x weights)
@@ -48,6 +48,9 @@ struct alignas(16) VTable {
 };
 static_assert(sizeof(VTable) <= 28 * 1024, "kernel parameters are limited to 32,764 bytes");
 
+// Source rows per TMA stage: 16-bit rows are twice as long, so half as many.
+__host__ __device__ constexpr int stage_rows(bool deep) { return deep ? RS / 2 : RS; }
+
 struct SmemLayout {
 	int row_bytes;    // bytes per staged source row
 	int ring, tmp, out, out_stride, xw, xf, xc, bars, total;
@@ -57,7 +60,7 @@ __host__ __device__ inline SmemLayout smem_layout(bool deep, int tile_w, int bpp
 	SmemLayout L;
 	L.row_bytes = NT * NV * (deep ? 2 : 1);
 	L.ring = 0;
-	L.tmp = L.ring + NS * RS * L.row_bytes;
+	L.tmp = L.ring + NS * stage_rows(deep) * L.row_bytes;
 	L.out = L.tmp + G * TMPS * 4 + 256;   // 64 zeroed floats: padded taps of the last row may read past it
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + G * L.out_stride;
@@ -288,35 +291,55 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 template <int C, bool DEEP, int XT>
 __device__ __noinline__ void pass2_short(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
-	for (int o = a.tid; o < a.tw * 4; o += NT) {
-		const int g = o & 3, xx = o >> 2;
-		if (g >= a.ng) continue;
-		const uint32_t w = a.sbase + a.xw + 4 * xx * a.xstride;
-		const uint32_t v0 = a.sbase + a.tmp + 4 * (g * TMPS + lds<int>(a.sbase + a.xf + 4 * xx) * C);
-		float wk[XT];
+	constexpr int U = 2;   // output pixels in flight per thread: their loads are issued together
+	const int total = a.tw * 4;
+	for (int o0 = a.tid; o0 < total; o0 += U * NT) {
+		int g[U], xx[U];
+		uint32_t w[U], v0[U];
+		bool live[U];
 #pragma unroll
-		for (int q = 0; q < XT / 4; ++q) {
-			const float4 wq = lds<float4>(w + 16 * q);
-			wk[4 * q] = wq.x; wk[4 * q + 1] = wq.y; wk[4 * q + 2] = wq.z; wk[4 * q + 3] = wq.w;
+		for (int u = 0; u < U; ++u) {
+			const int o = o0 + u * NT;
+			g[u] = o & 3;
+			xx[u] = o >> 2;
+			live[u] = o < total && g[u] < a.ng;
+			if (!live[u]) { xx[u] = 0; g[u] = 0; }          // a valid location: computed, not stored
+			w[u] = a.sbase + a.xw + 4 * xx[u] * a.xstride;
+			v0[u] = a.sbase + a.tmp + 4 * (g[u] * TMPS + lds<int>(a.sbase + a.xf + 4 * xx[u]) * C);
 		}
-		float acc[C];
+		float wk[U][XT];
 #pragma unroll
-		for (int ch = 0; ch < C; ++ch) acc[ch] = 0.0f;
+		for (int u = 0; u < U; ++u)
+#pragma unroll
+			for (int q = 0; q < XT / 4; ++q) {
+				const float4 wq = lds<float4>(w[u] + 16 * q);
+				wk[u][4 * q] = wq.x; wk[u][4 * q + 1] = wq.y; wk[u][4 * q + 2] = wq.z; wk[u][4 * q + 3] = wq.w;
+			}
+		float acc[U][C];
+#pragma unroll
+		for (int u = 0; u < U; ++u)
+#pragma unroll
+			for (int ch = 0; ch < C; ++ch) acc[u][ch] = 0.0f;
 #pragma unroll
 		for (int k = 0; k < XT; ++k) {
-			if (C == 4) {
-				const float4 p = lds<float4>(v0 + 16 * k);
-				acc[0] = fmaf(wk[k], p.x, acc[0]); acc[1 % C] = fmaf(wk[k], p.y, acc[1 % C]);
-				acc[2 % C] = fmaf(wk[k], p.z, acc[2 % C]); acc[3 % C] = fmaf(wk[k], p.w, acc[3 % C]);
-			} else if (C == 2) {
-				const float2 p = lds<float2>(v0 + 8 * k);
-				acc[0] = fmaf(wk[k], p.x, acc[0]); acc[1 % C] = fmaf(wk[k], p.y, acc[1 % C]);
-			} else {
 #pragma unroll
-				for (int ch = 0; ch < C; ++ch) acc[ch] = fmaf(wk[k], lds<float>(v0 + 4 * (C * k + ch)), acc[ch]);
+			for (int u = 0; u < U; ++u) {
+				if (C == 4) {
+					const float4 p = lds<float4>(v0[u] + 16 * k);
+					acc[u][0] = fmaf(wk[u][k], p.x, acc[u][0]); acc[u][1 % C] = fmaf(wk[u][k], p.y, acc[u][1 % C]);
+					acc[u][2 % C] = fmaf(wk[u][k], p.z, acc[u][2 % C]); acc[u][3 % C] = fmaf(wk[u][k], p.w, acc[u][3 % C]);
+				} else if (C == 2) {
+					const float2 p = lds<float2>(v0[u] + 8 * k);
+					acc[u][0] = fmaf(wk[u][k], p.x, acc[u][0]); acc[u][1 % C] = fmaf(wk[u][k], p.y, acc[u][1 % C]);
+				} else {
+#pragma unroll
+					for (int ch = 0; ch < C; ++ch) acc[u][ch] = fmaf(wk[u][k], lds<float>(v0[u] + 4 * (C * k + ch)), acc[u][ch]);
+				}
 			}
 		}
-		store_pixel<C, DEEP>(smem + a.outt + g * a.out_stride + xx * BPP, acc);
+#pragma unroll
+		for (int u = 0; u < U; ++u)
+			if (live[u]) store_pixel<C, DEEP>(smem + a.outt + g[u] * a.out_stride + xx[u] * BPP, acc[u]);
 	}
 	copy_out<BPP>(a);
 }
@@ -349,6 +372,7 @@ __global__ void __launch_bounds__(NT, (VARIANT == 0 && DEPTH <= 4 ? PICHA_FAST_M
 resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, int channels) {
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
+	constexpr int RSK = stage_rows(DEEP);        // rows per ring stage
 	constexpr int WS = (DEPTH + 3) & ~3;         // vertical weights per table row
 	const int bpp = channels * Depth<DEEP>::bytes;
 	const int tid = threadIdx.x;
@@ -361,7 +385,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	const int band = blockIdx.y;
 	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
 	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
-	const int nstages = (rhi - rlo + RS) / RS;
+	const int nstages = (rhi - rlo + RSK) / RSK;
 
 	const SmemLayout L = smem_layout(DEEP, t.tile_w, bpp, t.xstride);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);
@@ -371,10 +395,10 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	auto issue_stage = [&](int k) {
 		constexpr int BOXES = DEEP ? 2 : 1;      // TMA boxes are at most 256 elements wide
 		uint64_t *bar = bars + (k % NS);
-		mbar_expect_tx(bar, RS * L.row_bytes);
-		uint8_t *d = smem + L.ring + (k % NS) * RS * L.row_bytes;
+		mbar_expect_tx(bar, RSK * L.row_bytes);
+		uint8_t *d = smem + L.ring + (k % NS) * RSK * L.row_bytes;
 #pragma unroll
-		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RS * 1024, &smap, bar, word0 + b * 256, rlo + k * RS, blockIdx.z);
+		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RSK * 1024, &smap, bar, word0 + b * 256, rlo + k * RSK, blockIdx.z);
 	};
 
 	if (tid == 0) {
@@ -396,15 +420,15 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	int stage = -1, slot = NS - 1, rows_left = 0;   // uniform
 	uint32_t parity = 1;
 	uint32_t doff = 0;                              // shared address of this thread's words in the next row
-	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RS * 256 : 0) + ((tid * WPT) & 255));
+	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RSK * 256 : 0) + ((tid * WPT) & 255));
 	auto next_stage = [&]() {
 		__syncthreads();                  // every thread has finished the previous stage
 		++stage;
 		if (++slot == NS) { slot = 0; parity ^= 1; }
 		if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
 		mbar_wait(bars + slot, parity);
-		rows_left = RS;
-		doff = sbase + L.ring + slot * RS * L.row_bytes + thread_byte;
+		rows_left = RSK;
+		doff = sbase + L.ring + slot * RSK * L.row_bytes + thread_byte;
 	};
 	// Next row of the tile for this thread.  Called one row ahead of the row being accumulated, so
 	// the LDS latency is covered by this warp's own FMAs.  Past the band's last stage it does
