@@ -291,7 +291,10 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 template <int C, bool DEEP, int XT>
 __device__ __noinline__ void pass2_short(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
-	constexpr int U = 2;   // output pixels in flight per thread: their loads are issued together
+#ifndef PICHA_FAST_P2_U
+#define PICHA_FAST_P2_U 2
+#endif
+	constexpr int U = PICHA_FAST_P2_U;   // output pixels in flight per thread: their loads are issued together
 	const int total = a.tw * 4;
 	for (int o0 = a.tid; o0 < total; o0 += U * NT) {
 		int g[U], xx[U];
@@ -413,7 +416,9 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		sts(sbase + L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
 		sts(sbase + L.xc + 4 * i, t.xcount[x0 + i]);
 	}
-	if (tid < 64) sts(sbase + L.tmp + G * TMPS * 4 + 4 * tid, 0.0f);
+	// The unrolled horizontal pass multiplies zero-padded taps with whatever lies behind a column's
+	// window (row padding, rows of a partial group, the tail): make sure that is never a NaN.
+	for (int i = tid; i < G * TMPS + 64; i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
 	__syncthreads();   // tables and barrier initialisation are visible to every thread
 
 	// ---- ring consumer -------------------------------------------------------------------------
