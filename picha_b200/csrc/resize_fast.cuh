@@ -147,6 +147,47 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 		::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// The same on 32-bit shared-window addresses, for the out-of-line stage advance below.
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+	uint32_t ok, spins = 0;
+	do {
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			"selp.u32 %0, 1, 0, p;\n\t}"
+			: "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+		if (!ok && ++spins > (1u << 24)) __trap();   // a copy that never lands is a bug here: fail, do not hang
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y, int z) {
+	asm volatile(
+		"cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+		::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+// Stage transition of the ring, out of line: it runs once per 8 rows, and inlined into every copy of
+// the unrolled row body it would triple the size of the hot loop (instruction-cache misses showed
+// up as the top stall).  Issues stage `issue` (if >= 0) into its slot and waits for `wait_bar`.
+template <bool DEEP>
+__device__ __noinline__ void ring_advance(const CUtensorMap *map, uint32_t ring, uint32_t bars, int issue, int word0,
+                                          int row0, int img, uint32_t wait_bar, uint32_t parity, int tid) {
+	constexpr int RSK = stage_rows(DEEP);
+	constexpr int BOXES = DEEP ? 2 : 1;          // TMA boxes are at most 256 elements wide
+	constexpr int ROW_BYTES = NT * NV * (DEEP ? 2 : 1);
+	__syncthreads();                             // every thread has finished the previous stage
+	if (tid == 0 && issue >= 0) {
+		const uint32_t bar = bars + 8 * (issue % NS);
+		mbar_expect_tx_a(bar, RSK * ROW_BYTES);
+		const uint32_t d = ring + (issue % NS) * RSK * ROW_BYTES;
+#pragma unroll
+		for (int b = 0; b < BOXES; ++b) tma_load_3d_a(d + b * RSK * 1024, map, bar, word0 + b * 256, row0 + issue * RSK, img);
+	}
+	mbar_wait_a(wait_bar, parity);
+}
+
 // ---- unpack: exact float(v) * (1/max) in one FMA ----------------------------------------------
 // 0x4B000000 | v is the float 2^23 + v; fma(2^23 + v, inv, -2^23*inv) rounds the exact product
 // v*inv once, which is the reference's float(v) * inv (src/picha.h:98-105).
@@ -367,6 +408,9 @@ template <bool DEEP, int XS> __device__ __forceinline__ void run_pass2(const Pas
 	__syncthreads();           // pass 1 may overwrite the intermediate rows again
 }
 
+#ifndef PICHA_FAST_PAIR_UNROLL
+#define PICHA_FAST_PAIR_UNROLL 0
+#endif
 #ifndef PICHA_FAST_MIN_CTAS
 #define PICHA_FAST_MIN_CTAS 4
 #endif
@@ -427,11 +471,10 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	uint32_t doff = 0;                              // shared address of this thread's words in the next row
 	const int thread_byte = 4 * ((DEEP ? ((tid * WPT) >> 8) * RSK * 256 : 0) + ((tid * WPT) & 255));
 	auto next_stage = [&]() {
-		__syncthreads();                  // every thread has finished the previous stage
 		++stage;
 		if (++slot == NS) { slot = 0; parity ^= 1; }
-		if (tid == 0 && stage + NS - 1 < nstages) issue_stage(stage + NS - 1);
-		mbar_wait(bars + slot, parity);
+		ring_advance<DEEP>(&smap, sbase + L.ring, sbase + L.bars, stage + NS - 1 < nstages ? stage + NS - 1 : -1, word0, rlo,
+		                   blockIdx.z, sbase + L.bars + 8 * slot, parity, tid);
 		rows_left = RSK;
 		doff = sbase + L.ring + slot * RSK * L.row_bytes + thread_byte;
 	};
@@ -511,12 +554,21 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 					const int need = vt.ytab[y - vt.out_base];       // output y is complete after this row
 					int n = need - r + 1;
 					r = need + 1;
+#if PICHA_FAST_PAIR_UNROLL
 					for (; n >= 2; n -= 2) { row(s, wa, wb); row(s, wb, wa); }
 					if (n > 0) {
 						row(s, wa, wb);
 #pragma unroll
 						for (int i = 0; i < WPT; ++i) wa[i] = wb[i];
 					}
+#else
+#pragma unroll 1
+					for (; n > 0; --n) {                         // one copy of the row body per slot keeps the loop in the I-cache
+						row(s, wa, wb);
+#pragma unroll
+						for (int i = 0; i < WPT; ++i) wa[i] = wb[i];
+					}
+#endif
 					if (y >= y0) {
 						emit_row(gcount, acc[s]);
 						++gcount;
