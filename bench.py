@@ -226,13 +226,15 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     total_mpix = sum_over_ranks(out_mpix_rank)
     value = total_mpix / (ms_per_step / 1e3)
 
-    algo_bytes = n * (w["sw"] * w["sh"] + w["dw"] * w["dh"]) * bpp      # payload read + written per launch
-    launch_ms = sum(per) / len(per)                                       # one resize launch per step
+    algo_bytes = n * (w["sw"] * w["sh"] + w["dw"] * w["dh"]) * bpp      # payload read + written per step
+    launch_ms = sum(per) / len(per)                                       # the step's resize launches, back to back
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": profiled_traffic(key), "peak_source": peak_src,
-                "kernel": "resize (one launch per step)", "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel": f"resize kernel, {max(1, launches // max(1, args.steps))} launch(es) per step (one per group of row "
+                          "bands); bytes and time are per step",
+                "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_ms": round(launch_ms, 4), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4)}
 
     res = {"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "gpu_launches": launches,

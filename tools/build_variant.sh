@@ -6,7 +6,7 @@ name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/build/variants; mkdir -p $out/$name
 cd $root/picha_b200/csrc
-for f in api color_convert resize_exact synthetic resize_fast; do
+for f in $(ls *.cu | sed "s/\.cu$//"); do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off "$@" -c $f.cu -o $out/$name/$f.o &
 done
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -c tables.cc -o $out/$name/tables.o
