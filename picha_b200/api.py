@@ -23,6 +23,7 @@ from . import _native as N
 from .image import Image, PIXEL_ENUM, PIXEL_NAMES
 
 _pool = None
+_EMPTY = np.zeros(16, dtype=np.uint8)   # stands in for the data pointer of zero-byte images
 
 
 def _workers():
@@ -79,10 +80,10 @@ def _native_image(img):
 def _new_image(width, height, pixel):
     """newJsImage (src/picha.cc:119-133): row_stride, buffer of height*stride bytes."""
     stride = N.lib.picha_b200_row_stride(width, pixel)
-    data = np.empty(stride * height, dtype=np.uint8)
-    data[:] = 0
+    data = np.zeros(stride * height, dtype=np.uint8)
     img = Image({"width": width, "height": height, "pixel": PIXEL_NAMES[pixel], "stride": stride, "data": data})
-    return img, N.CImage(data.ctypes.data, stride, width, height, pixel)
+    base = data.ctypes.data if data.size else _EMPTY.ctypes.data   # never NULL; rows of zero bytes touch nothing
+    return img, N.CImage(base, stride, width, height, pixel)
 
 
 def _resize_options(opts):

@@ -47,18 +47,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn encode_fn() {
-	static EncodeTiledFn fn = nullptr;
-	static bool tried = false;
-	if (!tried) {
-		tried = true;
+	static const EncodeTiledFn fn = []() -> EncodeTiledFn {   // resolved once, thread-safe
 		void *p = nullptr;
 		cudaDriverEntryPointQueryResult q;
 		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
 		    q == cudaDriverEntryPointSuccess)
-			fn = reinterpret_cast<EncodeTiledFn>(p);
-		else
-			cudaGetLastError();
-	}
+			return reinterpret_cast<EncodeTiledFn>(p);
+		cudaGetLastError();
+		return nullptr;
+	}();
 	return fn;
 }
 

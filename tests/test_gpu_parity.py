@@ -404,6 +404,42 @@ def test_device_resident_batch_and_synthetic_parity(gpu):
         assert np.array_equal(grey.image(i).rows(), O.payload(want, ws, sw, sh, "greya"))
 
 
+def test_device_entry_with_unaligned_layout_uses_exact_kernel(gpu):
+    """Caller-owned device images with odd strides cannot be TMA-staged: the call still succeeds (exact kernel)."""
+    import torch
+    from picha_b200 import device as D
+    rng = np.random.default_rng(51)
+    sw, sh, dw, dh = 300, 200, 75, 50
+    img = rand_image(rng, sw, sh, "rgb")
+    src = D.DeviceBatch(2, sw, sh, "rgb", stride=sw * 3 + 1)       # 901-byte rows
+    dst = D.DeviceBatch(2, dw, dh, "rgb", stride=dw * 3 + 3)
+    for i in range(2):
+        src.upload(i, img)
+    D.resize(src, dst, "lanczos")
+    torch.cuda.synchronize()
+    want = oracle_resize(img, dw, dh, "lanczos", 1.0)
+    for i in range(2):
+        assert np.array_equal(dst.image(i).rows(), want.rows())
+
+
+def test_degenerate_and_error_cases_on_device(gpu):
+    P = gpu
+    empty = Image({"width": 0, "height": 3, "pixel": "rgb", "stride": 4, "data": np.zeros(12, np.uint8)})
+    out = P.colorConvertSync(empty, {"pixel": "rgba"})
+    assert out.width == 0 and out.height == 3
+    one = Image({"width": 1, "height": 1, "pixel": "greya", "data": np.array([7, 200, 0, 0], np.uint8)})
+    big = P.resizeSync(one, {"width": 3, "height": 2})
+    assert (big.rows()[:, 0::2] == 7).all() and (big.rows()[:, 1::2] == 200).all()
+    buf = np.zeros(64, np.uint8)
+    a = N.CImage(buf.ctypes.data, 16, 4, 4, 1)
+    b = N.CImage(buf.ctypes.data, 8, 2, 2, 0)
+    assert N.lib.picha_b200_resize(ctypes.byref(a), ctypes.byref(b), 0, 1.0) == N.ERR_FORMAT_MISMATCH
+    assert N.lib.picha_b200_color_convert(ctypes.byref(a), ctypes.byref(b), 0.3, 0.6, 0.1) == N.ERR_SIZE_MISMATCH
+    assert N.lib.picha_b200_resize_batch(-1, None, None, 0, 1.0, 0, 0) == N.ERR_INVALID_ARGUMENT
+    assert N.lib.picha_b200_init(99) == N.ERR_INVALID_ARGUMENT
+    assert N.lib.picha_b200_init(0) == 0
+
+
 def test_pinned_host_buffers(gpu):
     """Buffers from picha_b200_host_alloc take the no-staging path and give the same bytes."""
     P = gpu
