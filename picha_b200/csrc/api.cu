@@ -241,7 +241,10 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	size_t o_fxw = put_f(fx.w);
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
-		const int unit = align_pixels(pi.bytes);
+		// Tile widths: multiples of the 16-byte pixel group when the destination is the big side (vector
+		// stores on every tile); when the image shrinks by 2x or more the destination is small, so any
+		// multiple of 4 pixels will do and the source row of the tile can be filled to the brim.
+		const int unit = p->x.scale >= 2.0f ? 4 : align_pixels(pi.bytes);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
 			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 512);
 	}

@@ -264,9 +264,19 @@ template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) 
 		const int g = i / nvec, j = i - g * nvec;
 		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
 	}
-	const int tail0 = nvec << 4, tail = row_bytes - tail0;
+	// what 16-byte stores could not take: 4-byte stores where the row starts allow, bytes for the rest
+	int done = nvec << 4;
+	if ((((uintptr_t)a.gbase | (uintptr_t)a.dstride) & 3) == 0) {
+		const int nw = (row_bytes - done) >> 2;
+		for (int i = a.tid; i < a.ng * nw; i += NT) {
+			const int g = i / nw, j = done + 4 * (i - g * nw);
+			*reinterpret_cast<uint32_t *>(a.gbase + (long long)g * a.dstride + j) = lds<int>(a.sbase + a.outt + g * a.out_stride + j);
+		}
+		done += nw << 2;
+	}
+	const int tail = row_bytes - done;
 	for (int i = a.tid; i < a.ng * tail; i += NT) {
-		const int g = i / tail, j = tail0 + (i - g * tail);
+		const int g = i / tail, j = done + (i - g * tail);
 		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
 	}
 }
