@@ -70,9 +70,18 @@ int padded_depth(int d) {   // DEPTH the kernel is instantiated with
 
 int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap) {
 	const int limit = NT * NV / channels;   // source pixels one CTA row holds
+	// Among the widths whose source span fits, take the one that keeps both passes busiest: pass 1
+	// works on all NT*NV values of the staged row whether the tile needs them or not, pass 2 on
+	// rounds of NT (pixel, row) items.  The passes are weighted by which one dominates.
+	const bool down = dst_w > 0 && xfirst[dst_w - 1] + xcount[dst_w - 1] > dst_w;   // source wider than destination
+	const double w1 = down ? 0.7 : 0.3;
+	int best = 0;
+	double best_score = 0;
 	for (int tw = cap / unit * unit; tw >= unit; tw -= unit) {
 		bool ok = true;
-		for (int x0 = 0; x0 < dst_w && ok; x0 += tw) {
+		long long span_sum = 0;
+		int tiles = 0;
+		for (int x0 = 0; x0 < dst_w && ok; x0 += tw, ++tiles) {
 			const int x1 = (x0 + tw < dst_w ? x0 + tw : dst_w) - 1;
 			int hi = 0;   // the right edge is not monotone in x in general (trimmed zero taps): scan the tile
 			for (int x = x0; x <= x1; ++x)
@@ -81,10 +90,16 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 			for (int x = x0; x <= x1; ++x)
 				if (xfirst[x] < lo) lo = xfirst[x];
 			if (lo != xfirst[x0] || hi - xfirst[x0] / unit * unit > limit) ok = false;
+			span_sum += hi - lo;
 		}
-		if (ok) return tw;
+		if (!ok || tiles == 0) continue;
+		const double util1 = (double)span_sum / ((double)tiles * limit);
+		const int items = (tw < dst_w ? tw : dst_w) * 4;
+		const double util2 = (double)items / ((items + NT - 1) / NT * NT);
+		const double score = 1.0 / (w1 / util1 + (1.0 - w1) / util2);
+		if (score > best_score * 1.02) { best_score = score; best = tw; }   // prefer wider tiles on near-ties
 	}
-	return 0;
+	return best;
 }
 
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &tables,
