@@ -118,7 +118,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -218,8 +218,9 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     t1 = time.perf_counter()
     warm_launches = (P.launch_count() - launches0)
     launches = warm_launches * args.steps // (args.steps + args.warmup)
-    # clocks only over the timed part: the warm-up is at the start of [t0, t1]
-    clocks = sampler.stop(t1 - total_ms / 1e3 - 0.05, t1) if sampler else None
+    # clocks under load: from the first warm-up step to the end of the timed region (the timed part alone
+    # lasts tens of milliseconds, shorter than nvidia-smi's sampling period)
+    clocks = sampler.stop(t0, t1) if sampler else None
 
     ms_per_step = max_over_ranks(total_ms / args.steps)
     out_mpix_rank = n * w["dw"] * w["dh"] / 1e6
@@ -381,10 +382,11 @@ def run_convert_workload(key, args, rank, world, local_rank, with_e2e=True, with
 
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     launches0 = P.launch_count()
+    t0 = time.perf_counter()
     per, total_ms = time_device_steps(step, args.steps, args.warmup)
     t1 = time.perf_counter()
     launches = (P.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop(t1 - total_ms / 1e3 - 0.05, t1) if sampler else None
+    clocks = sampler.stop(t0, t1) if sampler else None
     ms_per_step = max_over_ranks(total_ms / args.steps)
     value = sum_over_ranks(n * w["w"] * w["h"] / 1e6) / (ms_per_step / 1e3)
     algo = n * w["w"] * w["h"] * (PIXEL_BYTES[w["src"]] + PIXEL_BYTES[w["dst"]])
@@ -483,7 +485,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(RESIZE_WORKLOADS) + list(CONVERT_WORKLOADS))
