@@ -212,31 +212,32 @@ template <bool DEEP> __device__ __forceinline__ void unpack8(const uint32_t *w, 
 	}
 }
 
-// pack: floor(clamp(f * max + 0.5)) without F2I (which costs several issue cycles here): adding 2^23
-// with round-toward-minus-infinity leaves floor(t) in the low mantissa bits; the clamp is done on
-// the biased float; byte/halfword merging with PRMT drops the exponent bits.
+// pack: floor(clamp(f * max + 0.5)).  The clamp is a saturate to [0, 1] on f itself (it folds into the
+// FMA that produced f as FFMA.SAT; clamping before or after the scaling gives the same integer), and the
+// float -> integer step avoids F2I (several issue cycles here): adding 2^23 with round-toward-minus-
+// infinity leaves floor(t) in the low mantissa bits; byte/halfword merging with PRMT drops the exponent.
 template <bool DEEP> __device__ __forceinline__ uint32_t pack_biased(float f) {
-	float t = __fadd_rd(fmaf(f, Depth<DEEP>::maxv, 0.5f), 8388608.0f);
-	t = fminf(fmaxf(t, 8388608.0f), 8388608.0f + Depth<DEEP>::maxv);
-	return __float_as_uint(t);
+	return __float_as_uint(__fadd_rd(fmaf(__saturatef(f), Depth<DEEP>::maxv, 0.5f), 8388608.0f));
 }
 
-template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint8_t *d, const float *acc) {
+// One packed pixel into the shared-memory output tile (shared-window address).
+template <int C, bool DEEP> __device__ __forceinline__ void store_pixel(uint32_t d, const float *acc) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	uint32_t v[C];
 #pragma unroll
 	for (int ch = 0; ch < C; ++ch) v[ch] = pack_biased<DEEP>(acc[ch]);
 	if (BPP == 4 && !DEEP) {
 		const uint32_t lo = __byte_perm(v[0], v[1 % C], 0x0040), hi = __byte_perm(v[2 % C], v[3 % C], 0x0040);
-		*reinterpret_cast<uint32_t *>(d) = __byte_perm(lo, hi, 0x5410);
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(d), "r"(__byte_perm(lo, hi, 0x5410)) : "memory");
 	} else if (BPP == 8) {
-		*reinterpret_cast<uint2 *>(d) = make_uint2(__byte_perm(v[0], v[1 % C], 0x5410), __byte_perm(v[2 % C], v[3 % C], 0x5410));
+		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(d), "r"(__byte_perm(v[0], v[1 % C], 0x5410)),
+		             "r"(__byte_perm(v[2 % C], v[3 % C], 0x5410)) : "memory");
 	} else if (DEEP) {
 #pragma unroll
-		for (int ch = 0; ch < C; ++ch) reinterpret_cast<uint16_t *>(d)[ch] = (uint16_t)v[ch];
+		for (int ch = 0; ch < C; ++ch) asm volatile("st.shared.u16 [%0], %1;" ::"r"(d + 2 * ch), "h"((uint16_t)v[ch]) : "memory");
 	} else {
 #pragma unroll
-		for (int ch = 0; ch < C; ++ch) d[ch] = (uint8_t)v[ch];
+		for (int ch = 0; ch < C; ++ch) asm volatile("st.shared.u8 [%0], %1;" ::"r"(d + ch), "r"(v[ch]) : "memory");
 	}
 }
 
@@ -290,7 +291,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		const bool two = RPT == 2 && g + 4 < a.ng;
 		const int cnt = lds<int>(a.sbase + a.xc + 4 * xx);
 		const uint32_t w = a.sbase + a.xw + 4 * xx * a.xstride;
-		const uint32_t v0 = a.sbase + a.tmp + 4 * (g * TMPS + lds<int>(a.sbase + a.xf + 4 * xx) * C);
+		const uint32_t v0 = a.sbase + a.tmp + 4 * g * TMPS + lds<int>(a.sbase + a.xf + 4 * xx);
 		const uint32_t v1 = v0 + (two ? 16 * TMPS : 0);
 		float acc0[C], acc1[C];
 #pragma unroll
@@ -330,7 +331,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 				}
 			}
 		}
-		uint8_t *d = smem + a.outt + g * a.out_stride + xx * BPP;
+		const uint32_t d = a.sbase + a.outt + g * a.out_stride + xx * BPP;
 		store_pixel<C, DEEP>(d, acc0);
 		if (two) store_pixel<C, DEEP>(d + 4 * a.out_stride, acc1);
 	}
@@ -359,7 +360,7 @@ __device__ __noinline__ void pass2_short(Pass2Args a) {
 			live[u] = o < total && g[u] < a.ng;
 			if (!live[u]) { xx[u] = 0; g[u] = 0; }          // a valid location: computed, not stored
 			w[u] = a.sbase + a.xw + 4 * xx[u] * a.xstride;
-			v0[u] = a.sbase + a.tmp + 4 * (g[u] * TMPS + lds<int>(a.sbase + a.xf + 4 * xx[u]) * C);
+			v0[u] = a.sbase + a.tmp + 4 * g[u] * TMPS + lds<int>(a.sbase + a.xf + 4 * xx[u]);
 		}
 		float wk[U][XT];
 #pragma unroll
@@ -393,7 +394,7 @@ __device__ __noinline__ void pass2_short(Pass2Args a) {
 		}
 #pragma unroll
 		for (int u = 0; u < U; ++u)
-			if (live[u]) store_pixel<C, DEEP>(smem + a.outt + g[u] * a.out_stride + xx[u] * BPP, acc[u]);
+			if (live[u]) store_pixel<C, DEEP>(a.sbase + a.outt + g[u] * a.out_stride + xx[u] * BPP, acc[u]);
 	}
 	copy_out<BPP>(a);
 }
@@ -467,7 +468,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	// this tile's horizontal tables -> shared memory
 	for (int i = tid; i < tw * t.xstride; i += NT) sts(sbase + L.xw + 4 * i, t.xw[(long long)x0 * t.xstride + i]);
 	for (int i = tid; i < tw; i += NT) {
-		sts(sbase + L.xf + 4 * i, t.xfirst[x0 + i] - sx0);
+		sts(sbase + L.xf + 4 * i, (t.xfirst[x0 + i] - sx0) * channels * 4);   // byte offset of the column's first tap in a row
 		sts(sbase + L.xc + 4 * i, t.xcount[x0 + i]);
 	}
 	// The unrolled horizontal pass multiplies zero-padded taps with whatever lies behind a column's
