@@ -255,30 +255,23 @@ struct Pass2Args {
 	int xstride, out_stride, dstride, tw, ng, tid;
 };
 
-// shared-memory tile -> global, 16 bytes per thread where the destination allows it
+// shared-memory tile -> global, 16 bytes per thread where the destination allows it (row by row:
+// no index division -- on upscales this loop moves most of the kernel's bytes)
 template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) {
 	__syncthreads();
 	const int row_bytes = a.tw * BPP;
 	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
 	const int nvec = vec ? row_bytes >> 4 : 0;
-	for (int i = a.tid; i < a.ng * nvec; i += NT) {
-		const int g = i / nvec, j = i - g * nvec;
-		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
-	}
-	// what 16-byte stores could not take: 4-byte stores where the row starts allow, bytes for the rest
 	int done = nvec << 4;
-	if ((((uintptr_t)a.gbase | (uintptr_t)a.dstride) & 3) == 0) {
-		const int nw = (row_bytes - done) >> 2;
-		for (int i = a.tid; i < a.ng * nw; i += NT) {
-			const int g = i / nw, j = done + 4 * (i - g * nw);
-			*reinterpret_cast<uint32_t *>(a.gbase + (long long)g * a.dstride + j) = lds<int>(a.sbase + a.outt + g * a.out_stride + j);
-		}
-		done += nw << 2;
-	}
-	const int tail = row_bytes - done;
-	for (int i = a.tid; i < a.ng * tail; i += NT) {
-		const int g = i / tail, j = done + (i - g * tail);
-		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
+	const bool word = (((uintptr_t)a.gbase | (uintptr_t)a.dstride) & 3) == 0;
+	const int nw = word ? (row_bytes - done) >> 2 : 0;
+	const int tail0 = done + (nw << 2);
+	for (int g = 0; g < a.ng; ++g) {
+		uint8_t *grow = a.gbase + (long long)g * a.dstride;
+		const uint32_t srow = a.sbase + a.outt + g * a.out_stride;
+		for (int j = a.tid; j < nvec; j += NT) reinterpret_cast<uint4 *>(grow)[j] = lds<uint4>(srow + 16 * j);
+		for (int j = a.tid; j < nw; j += NT) *reinterpret_cast<uint32_t *>(grow + done + 4 * j) = lds<int>(srow + done + 4 * j);
+		for (int j = tail0 + a.tid; j < row_bytes; j += NT) grow[j] = smem[a.outt + g * a.out_stride + j];
 	}
 }
 
