@@ -266,12 +266,26 @@ template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) 
 	const bool word = (((uintptr_t)a.gbase | (uintptr_t)a.dstride) & 3) == 0;
 	const int nw = word ? (row_bytes - done) >> 2 : 0;
 	const int tail0 = done + (nw << 2);
-	for (int g = 0; g < a.ng; ++g) {
-		uint8_t *grow = a.gbase + (long long)g * a.dstride;
-		const uint32_t srow = a.sbase + a.outt + g * a.out_stride;
-		for (int j = a.tid; j < nvec; j += NT) reinterpret_cast<uint4 *>(grow)[j] = lds<uint4>(srow + 16 * j);
-		for (int j = a.tid; j < nw; j += NT) *reinterpret_cast<uint32_t *>(grow + done + 4 * j) = lds<int>(srow + done + 4 * j);
-		for (int j = tail0 + a.tid; j < row_bytes; j += NT) grow[j] = smem[a.outt + g * a.out_stride + j];
+	if (nvec >= NT / 2) {                        // wide tiles (upscales): a row at a time
+		for (int g = 0; g < a.ng; ++g) {
+			uint8_t *grow = a.gbase + (long long)g * a.dstride;
+			const uint32_t srow = a.sbase + a.outt + g * a.out_stride;
+			for (int j = a.tid; j < nvec; j += NT) reinterpret_cast<uint4 *>(grow)[j] = lds<uint4>(srow + 16 * j);
+		}
+	} else {                                     // narrow tiles (downscales): all rows in one sweep
+		for (int i = a.tid; i < a.ng * nvec; i += NT) {
+			const int g = i / nvec, j = i - g * nvec;
+			reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
+		}
+	}
+	for (int i = a.tid; i < a.ng * nw; i += NT) {
+		const int g = i / nw, j = done + 4 * (i - g * nw);
+		*reinterpret_cast<uint32_t *>(a.gbase + (long long)g * a.dstride + j) = lds<int>(a.sbase + a.outt + g * a.out_stride + j);
+	}
+	const int tail = row_bytes - tail0;
+	for (int i = a.tid; i < a.ng * tail; i += NT) {
+		const int g = i / tail, j = tail0 + (i - g * tail);
+		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
 	}
 }
 
