@@ -114,6 +114,21 @@ def test_colour_fixture(gpu, fixtures):
     assert grey.equalPixels(box["img"])
 
 
+def test_readme_example_cfg1(gpu, fixtures):
+    """BASELINE cfg1 / README.md:33-34: test.jpeg decoded to rgb (50x50), resizeSync to 100x100, default options."""
+    P = gpu
+    rows = fixtures["test_jpeg_rgb"]
+    h, w, _ = rows.shape
+    image = Image({"width": w, "height": h, "pixel": "rgb"})
+    for y in range(h):
+        image.row(y)[:] = rows[y].reshape(-1)
+    want = oracle_resize(image, 100, 100, "cubic", np.float32(0.70))
+    got = P.resizeSync(image, {"width": 100, "height": 100})
+    assert got.width == 100 and got.height == 100 and got.pixel == "rgb" and got.stride == 300
+    assert got.equalPixels(want)                       # small image: the default is the bit-exact kernel
+    assert_resize_close(P.resizeSync(image, {"width": 100, "height": 100, "fast": True}), want, False, "cfg1 fast")
+
+
 def test_committed_reference_vectors(gpu, ref_vectors):
     """Outputs of the reference's own C++ (tests/golden/ref_vectors.npz) straight against the GPU."""
     P = gpu
@@ -438,6 +453,34 @@ def test_degenerate_and_error_cases_on_device(gpu):
     assert N.lib.picha_b200_resize_batch(-1, None, None, 0, 1.0, 0, 0) == N.ERR_INVALID_ARGUMENT
     assert N.lib.picha_b200_init(99) == N.ERR_INVALID_ARGUMENT
     assert N.lib.picha_b200_init(0) == 0
+
+
+def test_full_size_batch_properties(gpu):
+    """cfg3 shape as a device-resident batch (size-independent properties): images with equal content give
+    equal results wherever they sit in the batch, different content gives different results, a second
+    run is bit-identical, and image 0 equals the single-image host call."""
+    import torch
+    from picha_b200 import device as D
+    P = gpu
+    n, sw, sh, dw, dh = 12, 3840, 2160, 960, 540
+    src = D.DeviceBatch(n, sw, sh, "rgba")
+    half = D.DeviceBatch(n // 2, sw, sh, "rgba")
+    half.fill_synthetic(1237, first_image=40)
+    src.buf[:half.buf.numel()] = half.buf                      # images 0..5
+    src.buf[half.buf.numel():2 * half.buf.numel()] = half.buf  # images 6..11 = copies of 0..5
+    dst = D.DeviceBatch(n, dw, dh, "rgba")
+    D.resize(src, dst, "lanczos")
+    torch.cuda.synchronize()
+    first = dst.buf.clone()
+    D.resize(src, dst, "lanczos")
+    torch.cuda.synchronize()
+    assert torch.equal(first, dst.buf)
+    per = dst.buf[:n * dst.step].view(n, dst.step)
+    for i in range(n // 2):
+        assert torch.equal(per[i], per[i + n // 2]), i
+    assert not torch.equal(per[0], per[1])
+    host = P.resizeSync(src.image(0), {"width": dw, "height": dh, "filter": "lanczos"})
+    assert host.equalPixels(dst.image(0))
 
 
 def test_pinned_host_buffers(gpu):
