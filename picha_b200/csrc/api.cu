@@ -197,9 +197,10 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	// Rows of output per CTA band: as many as fit the exact kernel's shared-memory tile at the
 	// widest format (4 channels), starting from 8.
 	const size_t smem_budget = dev->smem_optin > 0 ? (size_t)dev->smem_optin : 48 * 1024;
-	int band_h = 8, max_rows = 0;
+	int band_h = 8, tile_w = 32, max_rows = 0;
 	std::vector<int> blo, brows;
-	for (;; band_h /= 2) {
+	auto fits = [&]() { return (size_t)max_rows * tile_w * 4 * sizeof(float) <= smem_budget; };
+	for (;;) {
 		const int nb = (dh + band_h - 1) / band_h;
 		blo.assign(nb, 0); brows.assign(nb, 0);
 		max_rows = 0;
@@ -214,9 +215,11 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 			blo[b] = lo; brows[b] = hi - lo + 1;
 			if (brows[b] > max_rows) max_rows = brows[b];
 		}
-		if ((size_t)max_rows * 32 * 4 * sizeof(float) <= smem_budget || band_h == 1) break;
+		if (fits() || band_h == 1) break;
+		band_h /= 2;
 	}
-	if ((size_t)max_rows * 32 * 4 * sizeof(float) > smem_budget) return PICHA_B200_ERR_UNSUPPORTED;
+	while (!fits() && tile_w > 1) tile_w /= 2;   // extreme downscales: one output row, few columns per CTA
+	if (!fits()) return PICHA_B200_ERR_UNSUPPORTED;
 	const int nb = (dh + band_h - 1) / band_h;
 	if (nb > 65535) return PICHA_B200_ERR_UNSUPPORTED;
 
@@ -258,6 +261,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->t.band_lo = ib + o_blo; p->t.band_rows = ib + o_brows;
 	p->t.xw = fb + o_xw; p->t.yw = fb + o_yw;
 	p->t.band_h = band_h;
+	p->t.tile_w = tile_w;
 	p->t.max_band_rows = max_rows;
 	p->ft.xfirst = ib + o_xfirst; p->ft.xcount = ib + o_xcount;
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;

@@ -25,6 +25,7 @@ struct ResizeTables {
 	// per band of `band_h` output rows: first source row touched and how many
 	const int *band_lo, *band_rows;
 	int band_h;         // output rows per CTA band
+	int tile_w;         // output columns per CTA
 	int max_band_rows;  // max over bands of band_rows
 };
 

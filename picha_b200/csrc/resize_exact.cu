@@ -1,6 +1,7 @@
 // Bit-exact fused two-pass resize: the parity anchor and the any-shape path.
 //
-// One CTA produces a tile of TW x band_h output pixels of one image:
+// One CTA produces a tile of tile_w x band_h output pixels of one image (32 x 8 unless the band's source
+// rows would not fit shared memory -- extreme downscales get narrower, shorter tiles):
 //   1. horizontal pass (src/resize.cc:105-119): for every source row the band's vertical taps
 //      touch, TW horizontally-filtered pixels go to shared memory as floats;
 //   2. vertical pass + pack (src/resize.cc:121-132) from shared memory.
@@ -14,7 +15,6 @@ namespace picha_b200 {
 
 namespace {
 
-constexpr int kTileW = 32;
 constexpr int kThreads = 256;
 
 template <int CH, bool DEEP>
@@ -23,8 +23,8 @@ resize_exact_kernel(DevBatch src, DevBatch dst, ResizeTables t) {
 	extern __shared__ float tmp[];   // [band rows][tw][CH]
 	constexpr int BPP = CH * Depth<DEEP>::bytes;
 
-	const int x0 = blockIdx.x * kTileW;
-	const int tw = min(kTileW, dst.width - x0);
+	const int x0 = blockIdx.x * t.tile_w;
+	const int tw = min(t.tile_w, dst.width - x0);
 	const int band = blockIdx.y;
 	const int y0 = band * t.band_h;
 	const int th = min(t.band_h, dst.height - y0);
@@ -74,7 +74,7 @@ resize_exact_kernel(DevBatch src, DevBatch dst, ResizeTables t) {
 
 template <int CH, bool DEEP>
 cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const ResizeTables &t, cudaStream_t stream) {
-	const size_t smem = (size_t)t.max_band_rows * kTileW * CH * sizeof(float);
+	const size_t smem = (size_t)t.max_band_rows * t.tile_w * CH * sizeof(float);
 	if (smem > (size_t)max_dynamic_smem()) return cudaErrorInvalidValue;
 	auto kern = resize_exact_kernel<CH, DEEP>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -85,7 +85,7 @@ cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const Resize
 		DevBatch s = src, d = dst;
 		s.base += (int64_t)z0 * src.step;
 		d.base += (int64_t)z0 * dst.step;
-		dim3 grid((dst.width + kTileW - 1) / kTileW, bands, nz);
+		dim3 grid((dst.width + t.tile_w - 1) / t.tile_w, bands, nz);
 		kern<<<grid, kThreads, smem, stream>>>(s, d, t);
 	}
 	return cudaGetLastError();

@@ -298,6 +298,19 @@ def real_valued_resize(arr, dw, dh, filt, fw):
     return np.einsum("yr,rxc->yxc", my, np.einsum("xs,rsc->rxc", mx, u))
 
 
+def test_resize_extreme_ratios(gpu):
+    """300:1 in either direction: ~1200-row (or -column) tap windows.  Only the bit-exact kernel takes these
+    (narrow, one-row tiles), whatever mode is asked for."""
+    P = gpu
+    rng = np.random.default_rng(61)
+    for pixel, (sw, sh, dw, dh) in itertools.product(("rgb", "r16g16b16a16"), [(64, 6000, 16, 20), (6000, 8, 20, 8)]):
+        img = rand_image(rng, sw, sh, pixel)
+        want = oracle_resize(img, dw, dh, "lanczos", 1.0)
+        for mode in ({}, {"fast": True}):
+            got = P.resizeSync(img, dict({"width": dw, "height": dh, "filter": "lanczos"}, **mode))
+            assert got.equalPixels(want), (pixel, sw, sh, dw, dh, mode)
+
+
 def test_resize_structured_inputs(gpu):
     """Constant rows, ramps, 0/max extremes, impulse (SURVEY 8d parity set)."""
     P = gpu
