@@ -416,6 +416,14 @@ int run_convert(const DevBatch &s, const DevBatch &d, int n, float r, float g, f
 	return 0;
 }
 
+// Host entry points run on whichever device they were asked for without changing the calling
+// thread's current device (the caller may be another CUDA user, e.g. PyTorch).
+struct DeviceGuard {
+	int prev = -1;
+	DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 struct Op {
 	bool resize;
 	int tag; float width; unsigned flags;   // resize
@@ -441,6 +449,7 @@ int submit(Device *dev, Lane *lane, const Op &op, const picha_b200_image &s, con
 int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *srcs, picha_b200_image *dsts) {
 	Device *dev = get_device(ordinal);
 	if (!dev) { g_last_error = "no such CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
+	DeviceGuard guard;                 // the caller's current device is restored on return
 	CU(cudaSetDevice(ordinal));
 	const int kLanes = n < 4 ? (n < 1 ? 1 : n) : 4;
 	Lane *lanes[4] = {nullptr, nullptr, nullptr, nullptr};
