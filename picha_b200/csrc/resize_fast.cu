@@ -79,7 +79,7 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 	double best_score = 0;
 	for (int tw = cap / unit * unit; tw >= unit; tw -= unit) {
 		bool ok = true;
-		long long span_sum = 0, warp_vals = 0;
+		long long span_sum = 0;
 		int tiles = 0;
 		for (int x0 = 0; x0 < dst_w && ok; x0 += tw, ++tiles) {
 			const int x1 = (x0 + tw < dst_w ? x0 + tw : dst_w) - 1;
@@ -91,12 +91,9 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 				if (xfirst[x] < lo) lo = xfirst[x];
 			if (lo != xfirst[x0] || hi - xfirst[x0] / unit * unit > limit) ok = false;
 			span_sum += hi - lo;
-			// pass 1 runs whole warps (32 threads x NV values): a warp past the window skips its arithmetic
-			const int vals = (hi - xfirst[x0] / unit * unit) * channels;
-			warp_vals += (vals + 32 * NV - 1) / (32 * NV) * (32 * NV);
 		}
 		if (!ok || tiles == 0) continue;
-		const double util1 = (double)span_sum * channels / (double)warp_vals;
+		const double util1 = (double)span_sum / ((double)tiles * limit);
 		const int items = (tw < dst_w ? tw : dst_w) * 4;
 		const double util2 = (double)items / ((items + NT - 1) / NT * NT);
 		const double score = 1.0 / (w1 / util1 + (1.0 - w1) / util2);

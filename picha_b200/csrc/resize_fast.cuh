@@ -446,10 +446,6 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	const int tw = min(t.tile_w, dst.width - x0);
 	const int sx0 = t.xfirst[x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
 	const int word0 = sx0 * bpp / 4;
-	// Warps whose 256 values lie entirely beyond the tile's source window keep step with the others
-	// (the ring and the groups are CTA-wide) but skip the arithmetic of pass 1.
-	const int span_values = (t.xfirst[x0 + tw - 1] + t.xcount[x0 + tw - 1] - sx0) * channels;
-	const bool warp_active = (tid & ~31) * NV < span_values;
 	// everything below is uniform across the CTA and comes from the constant bank
 	const int band = blockIdx.y;
 	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
@@ -553,19 +549,17 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		// `cur` holds row r's words, row r+1 is fetched into `nxt` meanwhile.
 		auto row = [&](int s, const uint32_t (&cur)[WPT], uint32_t (&nxt)[WPT]) {
 			fetch(nxt);
-			if (warp_active) {
-				float u[NV];
-				unpack8<DEEP>(cur, u, magic, inv);
-				const float *w = vt.wt + widx;                   // constant bank -> uniform registers
+			float u[NV];
+			unpack8<DEEP>(cur, u, magic, inv);
+			const float *w = vt.wt + widx;                       // constant bank -> uniform registers
 #pragma unroll
-				for (int j = 0; j < DEPTH - 1; ++j)
+			for (int j = 0; j < DEPTH - 1; ++j)
 #pragma unroll
-					for (int i = 0; i < NV; ++i) acc[(s + j) % DEPTH][i] = fmaf(w[j], u[i], acc[(s + j) % DEPTH][i]);
-				if (w[DEPTH - 1] != 0.0f) {                      // the newest output row is touched by few rows
+				for (int i = 0; i < NV; ++i) acc[(s + j) % DEPTH][i] = fmaf(w[j], u[i], acc[(s + j) % DEPTH][i]);
+			if (w[DEPTH - 1] != 0.0f) {                          // the newest output row is touched by few rows
 #pragma unroll
-					for (int i = 0; i < NV; ++i)
-						acc[(s + DEPTH - 1) % DEPTH][i] = fmaf(w[DEPTH - 1], u[i], acc[(s + DEPTH - 1) % DEPTH][i]);
-				}
+				for (int i = 0; i < NV; ++i)
+					acc[(s + DEPTH - 1) % DEPTH][i] = fmaf(w[DEPTH - 1], u[i], acc[(s + DEPTH - 1) % DEPTH][i]);
 			}
 			widx += WS;
 		};
