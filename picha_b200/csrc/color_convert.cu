@@ -30,13 +30,15 @@ template <bool SDEEP, bool DDEEP> __device__ __forceinline__ unsigned depth_conv
 }
 
 // One pixel, on integer channel values. SC/DC: channel counts. src/colorconvert.cc:24-134.
-template <int SC, bool SDEEP, int DC, bool DDEEP>
+// MAGIC: the luma inputs in[0..2] arrive as 0x4B000000 | v (the float 2^23 + v) straight out of a byte
+// permute, instead of as integers -- one instruction less per channel on the bandwidth path.
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool MAGIC = false>
 __device__ __forceinline__ void convert_pixel(const unsigned *in, unsigned *out, float rf, float gf, float bf) {
 	constexpr unsigned ONE = DDEEP ? 65535u : 255u;
 	if constexpr (SC >= 3 && DC <= 2) {          // 3->1, 3->2, 4->1, 4->2: luma (alpha ignored or passed through)
-		float r = unpack_value<SDEEP>(in[0]);
-		float g = unpack_value<SDEEP>(in[1]);
-		float b = unpack_value<SDEEP>(in[2]);
+		float r = MAGIC ? unpack_magic<SDEEP>(in[0]) : unpack_value<SDEEP>(in[0]);
+		float g = MAGIC ? unpack_magic<SDEEP>(in[1]) : unpack_value<SDEEP>(in[1]);
+		float b = MAGIC ? unpack_magic<SDEEP>(in[2]) : unpack_value<SDEEP>(in[2]);
 		float l = __fadd_rn(__fadd_rn(__fmul_rn(r, rf), __fmul_rn(g, gf)), __fmul_rn(b, bf));
 		out[0] = pack_value<DDEEP>(l);
 		if constexpr (DC == 2) out[1] = (SC == 4) ? depth_convert<SDEEP, DDEEP>(in[3]) : ONE;
@@ -67,14 +69,20 @@ __device__ __forceinline__ void convert_pixel(const unsigned *in, unsigned *out,
 constexpr int kWarps = 8;
 constexpr int kGroup = 128;   // pixels per warp step: 4 per lane
 
-// Channel i of a little-endian word array.
+// Channel i of a little-endian word array, zero-extended: one byte permute.
 template <bool DEEP> __device__ __forceinline__ unsigned word_get(const unsigned *w, int i) {
-	if (DEEP) return (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-	return (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
+	if (DEEP) return __byte_perm(w[i >> 1], 0u, (i & 1) ? 0x4432 : 0x4410);
+	return __byte_perm(w[i >> 2], 0u, 0x4440 + (i & 3));
 }
+// The same with 0x4B in the top byte: the bit pattern of the float 2^23 + value.
+template <bool DEEP> __device__ __forceinline__ unsigned word_get_magic(const unsigned *w, int i) {
+	if (DEEP) return __byte_perm(w[i >> 1], 0x4B000000u, (i & 1) ? 0x7432 : 0x7410);
+	return __byte_perm(w[i >> 2], 0x4B000000u, 0x7440 + (i & 3));
+}
+// Insert the low byte (halfword) of v as channel i; upper bits of v are ignored.
 template <bool DEEP> __device__ __forceinline__ void word_put(unsigned *w, int i, unsigned v) {
-	if (DEEP) w[i >> 1] |= v << (16 * (i & 1));
-	else w[i >> 2] |= v << (8 * (i & 3));
+	if (DEEP) w[i >> 1] = __byte_perm(w[i >> 1], v, (i & 1) ? 0x5410 : 0x3254);
+	else w[i >> 2] = __byte_perm(w[i >> 2], v, (i & 3) == 0 ? 0x3214 : (i & 3) == 1 ? 0x3240 : (i & 3) == 2 ? 0x3410 : 0x4210);
 }
 
 // A lane's N consecutive words of a warp tile, with the widest shared-memory access N allows
@@ -170,9 +178,11 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, fl
 #pragma unroll
 			for (int p = 0; p < 4; ++p) {
 				unsigned in[4], out[4];
+				constexpr bool LUMA = SC >= 3 && DC <= 2;
 #pragma unroll
-				for (int c = 0; c < SC; ++c) in[c] = word_get<SDEEP>(mine, p * SC + c);
-				convert_pixel<SC, SDEEP, DC, DDEEP>(in, out, rf, gf, bf);
+				for (int c = 0; c < SC; ++c)
+					in[c] = (LUMA && c < 3) ? word_get_magic<SDEEP>(mine, p * SC + c) : word_get<SDEEP>(mine, p * SC + c);
+				convert_pixel<SC, SDEEP, DC, DDEEP, LUMA>(in, out, rf, gf, bf);
 #pragma unroll
 				for (int c = 0; c < DC; ++c) word_put<DDEEP>(packed, p * DC + c, out[c]);
 			}

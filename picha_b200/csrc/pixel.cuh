@@ -33,11 +33,18 @@ template <bool DEEP> __device__ __forceinline__ float unpack_value(unsigned v) {
 	return __fmaf_rn(__uint_as_float(0x4B000000u | v), Depth<DEEP>::inv, -8388608.0f * Depth<DEEP>::inv);
 }
 
+// The same for a value that already is the bit pattern 0x4B000000 | v.
+template <bool DEEP> __device__ __forceinline__ float unpack_magic(unsigned magic_bits) {
+	return __fmaf_rn(__uint_as_float(magic_bits), Depth<DEEP>::inv, -8388608.0f * Depth<DEEP>::inv);
+}
+
+// Returns floor(t) in the low 23 bits; the bits above are the exponent of 2^23 (0x4B0...), which
+// every consumer drops: they store or merge only the low 8 / 16 bits.
 template <bool DEEP> __device__ __forceinline__ unsigned pack_value(float f) {
 	// (the reference's leading "0 +" only turns -0 into +0, which the clamp and floor do as well)
 	float t = __fadd_rn(__fmul_rn(f, Depth<DEEP>::maxv), 0.5f);
 	t = fmaxf(0.0f, fminf(Depth<DEEP>::maxv, t));   // NaN -> max, like std::min/std::max in the reference
-	return __float_as_uint(__fadd_rd(t, 8388608.0f)) & 0x7FFFFFu;
+	return __float_as_uint(__fadd_rd(t, 8388608.0f));
 }
 
 // Unaligned-safe channel load/store (subView bases are arbitrary byte offsets).
