@@ -423,6 +423,40 @@ def run_convert_workload(key, args, rank, world, local_rank, with_e2e=True, with
     return res
 
 
+def cfg1_latency(args):
+    """BASELINE cfg1 (README example): rgb 50x50 -> 100x100, default options, one blocking call through the
+    C-ABI with ordinary (pageable) host buffers.  Launch-latency bound: reported as latency, no roofline."""
+    import numpy as np
+    from picha_b200 import _native as N
+    from picha_b200.synthetic import fill_host
+    src = fill_host(50, 50, 3, 152, 1235, 0)
+    dst = np.zeros(300 * 100, np.uint8)
+    s = N.CImage(src.ctypes.data, 152, 50, 50, 0)
+    d = N.CImage(dst.ctypes.data, 300, 100, 100, 0)
+    tag, width = ctypes.c_int(0), ctypes.c_float(0)
+    N.check(N.lib.picha_b200_resolve_resize_options(0, 0, 0, 0.0, ctypes.byref(tag), ctypes.byref(width)))
+    times = []
+    for i in range(220):
+        t0 = time.perf_counter()
+        N.check(N.lib.picha_b200_resize(ctypes.byref(s), ctypes.byref(d), tag.value, width.value))
+        times.append(time.perf_counter() - t0)
+    times = sorted(times[20:])
+    out = {"median_us": round(times[len(times) // 2] * 1e6, 1), "p90_us": round(times[int(len(times) * 0.9)] * 1e6, 1),
+           "calls": len(times), "api": "picha_b200_resize (host buffers, blocking)"}
+    if not args.no_cpu:
+        import oracle as O
+        impl = "ref" if O.have_ref() else "port"
+        ct = []
+        for i in range(60):
+            t0 = time.perf_counter()
+            want, ws = O.resize(src, 152, 50, 50, "rgb", 100, 100, "cubic", width.value, impl)
+            ct.append(time.perf_counter() - t0)
+        ct.sort()
+        out["cpu_reference_median_us"] = round(ct[len(ct) // 2] * 1e6, 1)
+        out["bit_exact_vs_reference"] = bool(np.array_equal(dst.reshape(100, 300), O.payload(want, ws, 100, 100, "rgb")))
+    return out
+
+
 # ---- the reference arm: the reference's own CPU implementation on the host cores ----------------------
 
 def run_reference_arm(args):
@@ -542,6 +576,9 @@ def main():
         also[k] = {"value": round(r["value"], 1), "unit": "Mpix/s", "ms_per_step": round(r["ms_per_step"], 4),
                    "roofline_frac": r["roofline"]["frac"], "achieved_GBs": r["roofline"]["achieved"],
                    "images_per_gpu": r["images_per_gpu"], "cpu_baseline": r.get("cpu_baseline")}
+
+    if rank == 0 and world == 1 and args.also == "auto":
+        also["cfg1"] = cfg1_latency(args)
 
     if rank == 0:
         w = RESIZE_WORKLOADS.get(key) or CONVERT_WORKLOADS[key]
