@@ -241,7 +241,8 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	FastAxisX fx;
 	build_fast_y(p->y, kFastMaxDepth, fy);
 	build_fast_x(p->x, fx);
-	size_t o_fxw = put_f(fx.w);
+	size_t o_fxw = put_f(fx.w), o_fxfirst = put_i(fx.first), o_fxcount = put_i(fx.count);
+	size_t o_fxrow = put_i(fx.urow), o_fxuw = put_f(fx.uw);
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
 		// Tile widths: multiples of the 16-byte pixel group when the destination is the big side (vector
@@ -249,7 +250,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		// multiple of 4 pixels will do and the source row of the tile can be filled to the brim.
 		const int unit = p->x.scale >= 2.0f ? 4 : align_pixels(pi.bytes);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
-			: fast_tile_width(p->x.first.data(), p->x.count.data(), dw, pi.channels, unit, 512);
+			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, 512);
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
@@ -263,8 +264,10 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->t.band_h = band_h;
 	p->t.tile_w = tile_w;
 	p->t.max_band_rows = max_rows;
-	p->ft.xfirst = ib + o_xfirst; p->ft.xcount = ib + o_xcount;
+	p->ft.xfirst = ib + o_fxfirst; p->ft.xcount = ib + o_fxcount;
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
+	p->ft.xtaps = fx.taps;
+	p->ft.xrow = ib + o_fxrow; p->ft.xuw = fb + o_fxuw; p->ft.xunique = fx.unique;
 	p->ft.xshort = fx.taps <= 4 ? 4 : (fx.taps <= 8 ? 8 : 0);
 
 	dev->plans[key] = p;

@@ -45,6 +45,10 @@ struct FastTables {
 	const int *xfirst, *xcount;
 	const float *xw;
 	int xstride;
+	int xtaps;    // most taps of any column
+	const int *xrow;     // [dst] the column's row in xuw
+	const float *xuw;    // [xunique][xstride] distinct weight rows
+	int xunique;
 	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA

@@ -1,0 +1,563 @@
+// Downscaling variant of the fast resize path (reference: src/resize.cc:66-134); design notes in
+// resize_fast.cu and DESIGN.md section 5.3.  Included by the resize_down_*.cu instantiation units.
+//
+// Compared with the generic kernel of resize_fast.cuh this one is built around the instruction
+// budget of the vertical pass, which is what bounds a wide-filter downscale on this part:
+//   * 64 threads x 16 channel values per row: per-row control and weight loads are amortised
+//     over twice as many FMAs.
+//   * No unpack arithmetic.  A byte (or 16-bit value) v moved into the low bits of an otherwise
+//     zero word IS the float v * 2^-149 (a subnormal, exact), and the FMA pipe takes subnormal
+//     inputs at full speed: one PRMT per value replaces PRMT + FMA.  The vertical weights carry
+//     2^120 so the sums are ordinary normal floats (w*v * 2^-29); the horizontal weights carry
+//     2^29 / max, so the second pass lands on the [0, 1] scale the pack expects.  Every product is
+//     formed exactly inside the FMA, so nothing is lost relative to unpacking first.
+//   * Accumulator slots are fixed (output row y lives in slot y % DEPTH) and the host lays the
+//     weights of a source row out in slot order: the row body is the same code for every row --
+//     no rotation by unrolling, no per-row branches; only the (rare) emit picks a slot.
+//   * The row loop counts down to the next event (an output row completes, or the ring stage
+//     ends) in one counter; rows are prefetched one ahead into alternating registers.
+//   * Ring stages are handed back through `empty` mbarriers (no CTA-wide barrier in pass 1).
+//   * Pass 2 uses packed FMAs (fma.rn.f32x2: two channels per instruction, weights stored
+//     duplicated in shared memory) and stores 4- and 8-byte pixels straight to global memory.
+#ifndef PICHA_B200_RESIZE_DOWN_CUH
+#define PICHA_B200_RESIZE_DOWN_CUH
+
+#include "resize_fast.cuh"
+
+namespace picha_b200 {
+namespace down {
+
+using fast::lds;
+using fast::sts;
+using fast::smem;
+using fast::smem_u32;
+using fast::VTable;
+using fast::kMaxBands;
+using fast::kYtabMax;
+using fast::kWtMax;
+
+constexpr int NT = 64;             // threads per CTA
+constexpr int NV = 16;             // channel values of one source row owned by a thread
+constexpr int ROWV = NT * NV;      // values per staged row (the tile geometry of the generic kernel)
+static_assert(ROWV == fast::NT * fast::NV, "tile widths are planned once for both kernels");
+constexpr int G = 4;               // output rows per pass-2 group
+constexpr int TMPS = ROWV + 4;     // floats per intermediate row (+4: rows land 4 banks apart)
+#ifndef PICHA_DOWN_NS
+#define PICHA_DOWN_NS 2
+#endif
+constexpr int NS = PICHA_DOWN_NS;  // ring stages
+constexpr int STAGE_BYTES = 8192;  // 8 rows of 1024 bytes (u8) or 4 rows of 2048 bytes (u16)
+constexpr int kVExp = 120;         // vertical weights are scaled by 2^kVExp
+constexpr int kMaxDepth = 8;
+
+__host__ __device__ constexpr int stage_rows(bool deep) { return deep ? 4 : 8; }
+
+struct SmemLayout {
+	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, bars, total;
+};
+
+// nb: blocks of 4 horizontal taps; wrows: weight rows held in shared memory (the plan's distinct
+// rows, or one per column of the tile); direct: pixels go straight to global memory (no output tile).
+__host__ __device__ inline SmemLayout smem_layout(int tile_w, int bpp, int channels, int nb, int wrows, bool direct) {
+	SmemLayout L;
+	L.ring = 0;
+	L.tmp = L.ring + NS * STAGE_BYTES;
+	// Every column runs the same nb blocks of taps; a column with a shorter window (image edges) reads on
+	// behind it with zero weights -- into the next row of the group or, from the last row, into this
+	// zeroed tail (at most 4 * nb pixels).
+	L.tmp_floats = G * TMPS + (4 * nb * channels + 63) / 64 * 64;
+	L.out = L.tmp + L.tmp_floats * 4;
+	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
+	L.xw = L.out + (direct ? 0 : G * L.out_stride);
+	L.xs2 = 8 * nb + 4;                    // floats per column: duplicated weights, rows 4 banks apart
+	L.xf = L.xw + wrows * L.xs2 * 4;         // per column: {byte offset of the first tap in a row, of the weight row}
+	L.bars = L.xf + tile_w * 8;
+	L.total = L.bars + 2 * NS * 8;
+	return L;
+}
+
+struct DownArgs {
+	float xscale;   // factor on the horizontal weights: 2^(149 - kVExp) / max
+	int nb;         // blocks of 4 horizontal taps every column is padded to
+	int direct;     // 4- and 8-byte pixels with an aligned destination: stored from registers
+	int wrows;      // weight rows in shared memory: FastTables::xunique (shared by all columns) or tile_w (one each)
+	int uniq;       // which of the two
+};
+
+__device__ __forceinline__ void mbar_init_a(uint32_t bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+typedef unsigned long long u64;
+__device__ __forceinline__ void ffma2(u64 &acc, u64 a, u64 b) {
+	asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void lds_2x64(uint32_t addr, u64 &lo, u64 &hi) {
+	asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ u64 lds_64(uint32_t addr) {
+	u64 v;
+	asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ u64 pair(float lo, float hi) {
+	u64 v;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+	return v;
+}
+__device__ __forceinline__ void unpair(u64 v, float &lo, float &hi) {
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
+// Stage transition of the ring (once per 8 KB of source).  A warp that has read the last row of a
+// stage counts itself out on the stage's counter; the last warp to do so refills the slot with the
+// stage NS ahead -- nobody ever waits for another warp -- and then everyone waits for the next
+// stage to land (normally it has).  No loop runs under a per-thread condition here: that would make
+// the compiler treat the caller's loop state as divergent and move the vertical weights out of the
+// uniform registers.
+struct RingState {
+	int stage, slot, nstages;
+	uint32_t parity;
+};
+
+template <bool DEEP>
+__device__ __forceinline__ RingState ring_advance(const CUtensorMap *map, uint32_t ring, uint32_t bars, RingState rs, int word0,
+                                                  int row0, int img, int tid) {
+	constexpr int RSK = stage_rows(DEEP);
+	constexpr int BOXES = DEEP ? 2 : 1;          // TMA boxes are at most 256 elements wide
+	const int prev = rs.slot;
+	if (rs.stage >= 0 && rs.stage + NS < rs.nstages) {
+		__syncwarp();
+		if ((tid & 31) == 0) {
+			uint32_t old;
+			asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bars + 8 * (NS + prev)) : "memory");
+			if (old == NT / 32 - 1) {
+				asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 8 * (NS + prev)), "r"(0) : "memory");
+				fast::mbar_expect_tx_a(bars + 8 * prev, STAGE_BYTES);
+#pragma unroll
+				for (int b = 0; b < BOXES; ++b)
+					fast::tma_load_3d_a(ring + prev * STAGE_BYTES + b * RSK * 1024, map, bars + 8 * prev, word0 + b * 256,
+					                    row0 + (rs.stage + NS) * RSK, img);
+			}
+		}
+	}
+	++rs.stage;
+	if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
+	fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
+	return rs;
+}
+
+// ---- pass 2 -----------------------------------------------------------------------------------
+struct Pass2Args {
+	uint32_t sbase;
+	int tmp, xw, xf, outt;
+	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
+	int xs2, out_stride, dstride, tw, ng, tid, direct, nb;
+};
+
+// shared-memory output tile -> global memory, 16 bytes per thread where the destination allows it
+template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) {
+	__syncthreads();
+	const int row_bytes = a.tw * BPP;
+	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
+	const int nvec = vec ? row_bytes >> 4 : 0;
+	const int done = nvec << 4;
+	for (int i = a.tid; i < a.ng * nvec; i += NT) {
+		const int g = i / nvec, j = i - g * nvec;
+		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
+	}
+	const int tail = row_bytes - done;
+	for (int i = a.tid; i < a.ng * tail; i += NT) {
+		const int g = i / tail, j = done + (i - g * tail);
+		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
+	}
+}
+
+// Accumulators of one output pixel and one block of 4 taps into them.  Weights come duplicated
+// ({w, w} pairs) so that two channels share a packed FMA; odd channel counts keep two partial sums
+// per channel (even / odd taps) to shorten the dependency chains.
+template <int C> struct PixelAcc;
+template <> struct PixelAcc<4> {
+	u64 a01 = 0, a23 = 0;
+	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
+		u64 w0, w1, w2, w3, p0, p1, p2, p3, p4, p5, p6, p7;
+		lds_2x64(w, w0, w1);
+		lds_2x64(w + 16, w2, w3);
+		lds_2x64(v, p0, p1);
+		lds_2x64(v + 16, p2, p3);
+		lds_2x64(v + 32, p4, p5);
+		lds_2x64(v + 48, p6, p7);
+		ffma2(a01, p0, w0); ffma2(a23, p1, w0);
+		ffma2(a01, p2, w1); ffma2(a23, p3, w1);
+		ffma2(a01, p4, w2); ffma2(a23, p5, w2);
+		ffma2(a01, p6, w3); ffma2(a23, p7, w3);
+	}
+	__device__ __forceinline__ void result(float *f) const { unpair(a01, f[0], f[1]); unpair(a23, f[2], f[3]); }
+};
+template <> struct PixelAcc<2> {
+	u64 e = 0, od = 0;
+	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
+		u64 w0, w1, w2, w3;
+		lds_2x64(w, w0, w1);
+		lds_2x64(w + 16, w2, w3);
+		const u64 p0 = lds_64(v), p1 = lds_64(v + 8), p2 = lds_64(v + 16), p3 = lds_64(v + 24);
+		ffma2(e, p0, w0); ffma2(od, p1, w1);
+		ffma2(e, p2, w2); ffma2(od, p3, w3);
+	}
+	__device__ __forceinline__ void result(float *f) const {
+		float e0, e1, o0, o1;
+		unpair(e, e0, e1);
+		unpair(od, o0, o1);
+		f[0] = e0 + o0;
+		f[1] = e1 + o1;
+	}
+};
+template <> struct PixelAcc<3> {
+	u64 a01 = 0, b01 = 0;
+	float a2 = 0.0f, b2 = 0.0f;
+	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
+		u64 w0, w1, w2, w3;
+		lds_2x64(w, w0, w1);
+		lds_2x64(w + 16, w2, w3);
+		float s0, s1, s2, s3, d;
+		unpair(w0, s0, d); unpair(w1, s1, d); unpair(w2, s2, d); unpair(w3, s3, d);
+		float q[12];
+#pragma unroll
+		for (int i = 0; i < 12; ++i) q[i] = lds<float>(v + 4 * i);
+		ffma2(a01, pair(q[0], q[1]), w0); a2 = fmaf(s0, q[2], a2);
+		ffma2(b01, pair(q[3], q[4]), w1); b2 = fmaf(s1, q[5], b2);
+		ffma2(a01, pair(q[6], q[7]), w2); a2 = fmaf(s2, q[8], a2);
+		ffma2(b01, pair(q[9], q[10]), w3); b2 = fmaf(s3, q[11], b2);
+	}
+	__device__ __forceinline__ void result(float *f) const {
+		float x0, x1, y0, y1;
+		unpair(a01, x0, x1);
+		unpair(b01, y0, y1);
+		f[0] = x0 + y0;
+		f[1] = x1 + y1;
+		f[2] = a2 + b2;
+	}
+};
+template <> struct PixelAcc<1> {
+	float e = 0.0f, od = 0.0f;
+	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
+		u64 w0, w1, w2, w3;
+		lds_2x64(w, w0, w1);
+		lds_2x64(w + 16, w2, w3);
+		float s0, s1, s2, s3, d;
+		unpair(w0, s0, d); unpair(w1, s1, d); unpair(w2, s2, d); unpair(w3, s3, d);
+		e = fmaf(s0, lds<float>(v), e);
+		od = fmaf(s1, lds<float>(v + 4), od);
+		e = fmaf(s2, lds<float>(v + 8), e);
+		od = fmaf(s3, lds<float>(v + 12), od);
+	}
+	__device__ __forceinline__ void result(float *f) const { f[0] = e + od; }
+};
+
+// A thread produces P2U output pixels at a time (same row of the group, columns 16 apart): their
+// loads and FMA chains interleave, which is what hides the shared-memory and FMA latencies here --
+// there are only two or three warps per scheduler.  Every column runs the same `nb` blocks of taps
+// (weights are zero-padded; what lies behind a short window is finite: see the kernel).
+#ifndef PICHA_DOWN_P2U
+#define PICHA_DOWN_P2U 4
+#endif
+template <int C, bool DEEP>
+__device__ __noinline__ void pass2(Pass2Args a) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	constexpr int U = PICHA_DOWN_P2U;
+	const int total = a.tw * 4;
+	const int g = a.tid & 3;                       // NT is a multiple of 4: the same row for every item
+	const uint32_t vrow = a.sbase + a.tmp + 4 * g * TMPS;
+	for (int o0 = a.tid; o0 < total; o0 += U * NT) {
+		int xx[U];
+		bool live[U];
+		uint32_t w[U], v[U];
+		PixelAcc<C> acc[U];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int o = o0 + u * NT;
+			live[u] = o < total && g < a.ng;
+			xx[u] = live[u] ? o >> 2 : 0;            // idle slots recompute column 0 and store nothing
+			const uint2 e = lds<uint2>(a.sbase + a.xf + 8 * xx[u]);
+			v[u] = vrow + e.x;
+			w[u] = a.sbase + a.xw + e.y;
+		}
+		for (int kb = 0; kb < a.nb; ++kb) {
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				acc[u].block(w[u], v[u]);
+				w[u] += 32;
+				v[u] += 16 * C;
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			if (!live[u]) continue;
+			float f[C];
+			acc[u].result(f);
+			if ((BPP == 4 || BPP == 8) && a.direct) {
+				uint32_t pv[C];
+#pragma unroll
+				for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
+				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * BPP;
+				if (BPP == 4 && !DEEP) {
+					const uint32_t lo = __byte_perm(pv[0], pv[1 % C], 0x0040), hi = __byte_perm(pv[2 % C], pv[3 % C], 0x0040);
+					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(lo, hi, 0x5410);
+				} else if (BPP == 4) {
+					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(pv[0], pv[1 % C], 0x5410);
+				} else {
+					*reinterpret_cast<uint2 *>(gp) = make_uint2(__byte_perm(pv[0], pv[1 % C], 0x5410), __byte_perm(pv[2 % C], pv[3 % C], 0x5410));
+				}
+			} else {
+				fast::store_pixel<C, DEEP>(a.sbase + a.outt + g * a.out_stride + xx[u] * BPP, f);
+			}
+		}
+	}
+	if (!((BPP == 4 || BPP == 8) && a.direct)) copy_out<BPP>(a);
+}
+
+// ---- the kernel -------------------------------------------------------------------------------
+#ifndef PICHA_DOWN_MINB
+#define PICHA_DOWN_MINB(D) ((D) <= 4 ? 6 : (D) <= 6 ? 5 : 4)
+#endif
+
+template <int DEPTH, bool DEEP, int C>
+__global__ void __launch_bounds__(NT, PICHA_DOWN_MINB(DEPTH))
+resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
+                   const __grid_constant__ VTable vt, DownArgs da) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	constexpr int RSK = stage_rows(DEEP);
+	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
+	constexpr int WPT = DEEP ? 8 : 4;            // 32-bit words of a source row per thread
+	const int tid = threadIdx.x;
+
+	const int x0 = blockIdx.x * t.tile_w;
+	const int tw = min(t.tile_w, dst.width - x0);
+	const int sx0 = t.xfirst[x0] / t.align_px * t.align_px;   // tile origin: 16-byte aligned in the row (TMA box start)
+	const int word0 = sx0 * BPP / 4;
+	const int band = blockIdx.y;
+	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
+	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
+
+	const bool direct = (BPP == 4 || BPP == 8) && da.direct;
+	const SmemLayout L = smem_layout(t.tile_w, BPP, C, da.nb, da.wrows, direct);
+	uint32_t sbase = smem_u32(smem);
+	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
+	const uint32_t bars = sbase + L.bars;          // full[NS] mbarriers, then NS hand-back counters
+	const uint32_t ring = sbase + L.ring;
+
+	RingState rs;
+	rs.stage = -1; rs.slot = NS - 1; rs.parity = 1;
+	rs.nstages = (rhi + 1 - rlo) / RSK + 1;        // rows rlo .. rhi + 1: every row is prefetched one ahead
+
+	if (tid == 0) {
+		for (int i = 0; i < NS; ++i) {
+			mbar_init_a(bars + 8 * i, 1);
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 8 * (NS + i)), "r"(0) : "memory");   // hand-back counter
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		constexpr int BOXES = DEEP ? 2 : 1;
+		for (int k = 0; k < NS && k < rs.nstages; ++k) {
+			fast::mbar_expect_tx_a(bars + 8 * k, STAGE_BYTES);
+#pragma unroll
+			for (int b = 0; b < BOXES; ++b)
+				fast::tma_load_3d_a(ring + k * STAGE_BYTES + b * RSK * 1024, &smap, bars + 8 * k, word0 + b * 256, rlo + k * RSK, blockIdx.z);
+		}
+	}
+	// this tile's horizontal tables -> shared memory: weights scaled and duplicated (packed-FMA operands)
+	const bool uniq = da.uniq != 0;                // the plan's distinct rows, else one row per column
+	const float *wsrc = uniq ? t.xuw : t.xw + (long long)x0 * t.xstride;
+	const int wrows = uniq ? da.wrows : tw;
+	for (int i = tid; i < wrows * da.nb * 4; i += NT) {
+		const int row = i / (da.nb * 4), k = i - row * (da.nb * 4);
+		const float w = k < t.xstride ? wsrc[(long long)row * t.xstride + k] * da.xscale : 0.0f;
+		asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
+	}
+	for (int i = tid; i < tw; i += NT) {
+		const int first = (t.xfirst[x0 + i] - sx0) * C * 4;    // byte offset of the column's first tap in a row
+		const int wrow = uniq ? t.xrow[x0 + i] : i;
+		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"(first), "r"(wrow * L.xs2 * 4) : "memory");
+	}
+	// padded taps multiply whatever lies behind a column's window by zero: make sure that is never a NaN
+	for (int i = tid; i < L.tmp_floats; i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
+	__syncthreads();
+
+	// This thread's share of a staged row: four chunks of 4 values, 256 values apart (consecutive
+	// lanes read consecutive words and, in the emit, write consecutive float4s: no bank conflicts).
+	const uint32_t thread_off = DEEP ? 8 * tid : 4 * tid;
+	uint32_t faddr = 0;     // shared address of this thread's first chunk in the next row to fetch
+	int fleft = 0;          // rows left to fetch in the current stage
+	auto load_row = [&](uint32_t (&w)[WPT]) {
+		if (DEEP) {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint2 v = lds<uint2>(faddr + (q >> 1) * (RSK * 1024) + (q & 1) * 512);
+				w[(2 * q) % WPT] = v.x; w[(2 * q + 1) % WPT] = v.y;
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; ++q) w[q] = (uint32_t)lds<int>(faddr + 256 * q);
+		}
+		faddr += 1024;
+	};
+	auto advance = [&]() {
+		rs = ring_advance<DEEP>(&smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
+		fleft = RSK;
+		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
+	};
+
+	float acc[DEPTH][NV];
+#pragma unroll
+	for (int j = 0; j < DEPTH; ++j)
+#pragma unroll
+		for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
+
+	// One source row into every open output row.  The value is used as the subnormal float its bits
+	// already are (see the header); weights come from the constant bank as uniform operands.
+	auto body = [&](const uint32_t (&cur)[WPT], const float (&w)[DEPTH]) {
+#pragma unroll
+		for (int i = 0; i < NV; ++i) {
+			uint32_t bits;
+			if (DEEP) bits = (i & 1) ? cur[(i >> 1) % WPT] >> 16 : cur[(i >> 1) % WPT] & 0xFFFFu;
+			else bits = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4440 + (i & 3));
+			const float u = __uint_as_float(bits);
+#pragma unroll
+			for (int j = 0; j < DEPTH; ++j) acc[j][i] = fmaf(w[j], u, acc[j][i]);
+		}
+	};
+	// The weights of a row are fetched from the constant bank into uniform registers one row ahead,
+	// like the data: issued right in front of their first use, the load's latency stalls every row.
+	auto load_w = [&](float (&w)[DEPTH], int widx) {
+#pragma unroll
+		for (int j = 0; j < DEPTH; ++j) w[j] = vt.wt[widx + j];
+	};
+
+	Pass2Args pa;
+	pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
+	pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
+	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * BPP;
+	const uint32_t my_tmp = sbase + L.tmp + tid * 16;
+
+	uint32_t ra[WPT], rb[WPT];
+	float wa[DEPTH], wb[DEPTH];
+	advance();
+	load_row(ra);
+	--fleft;
+	int r = rlo;                                   // the row held in ra
+	int y = vt.band_ys[band];                      // oldest open output row
+	int yslot = y % DEPTH;
+	int widx = (rlo - vt.row_base) * WS;           // weights of the row after the one held in ra
+	load_w(wa, widx);
+	widx += WS;
+	int gcount = 0;
+	int need = vt.ytab[y - vt.out_base];           // last source row of output y (fetched one output ahead)
+	while (y < y1) {
+		int n = need - r + 1;                      // output y is complete after this many more rows
+		r += n;
+		need = vt.ytab[y + 1 - vt.out_base];
+		while (n > 0) {
+			if (fleft == 0) advance();
+			int m = min(n, fleft);
+			n -= m;
+			fleft -= m;
+			do {
+				load_row(rb);
+				load_w(wb, widx);
+				body(ra, wa);
+				widx += WS;
+				if (--m == 0) {
+#pragma unroll
+					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+					for (int j = 0; j < DEPTH; ++j) wa[j] = wb[j];
+					break;
+				}
+				load_row(ra);
+				load_w(wa, widx);
+				body(rb, wb);
+				widx += WS;
+			} while (--m);
+		}
+		// emit: slot y % DEPTH is final; it becomes the slot of output y + DEPTH
+#pragma unroll
+		for (int j = 0; j < DEPTH; ++j) {
+			if (j == yslot) {
+				if (y >= y0) {
+#if PICHA_DOWN_EMIT_SCALAR
+#pragma unroll
+					for (int i = 0; i < NV; ++i) sts(my_tmp + gcount * (TMPS * 4) + (i >> 2) * 1024 + (i & 3) * 4, acc[j][i]);
+#else
+#pragma unroll
+					for (int q = 0; q < 4; ++q)
+						sts(my_tmp + gcount * (TMPS * 4) + q * 1024,
+						    make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]));
+#endif
+					++gcount;
+				}
+				// in place (tied operand, x * 0): a plain "= 0.0f" makes new values that ptxas pairs up for CS2R and
+				// then shuffles every accumulator of the kernel between two register assignments per output row
+#pragma unroll
+				for (int i = 0; i < NV; ++i) asm volatile("mul.f32 %0, %0, 0f00000000;" : "+f"(acc[j][i]));
+			}
+		}
+		++y;
+		if (++yslot == DEPTH) yslot = 0;
+		if (gcount == G || (y == y1 && gcount > 0)) {
+			pa.ng = gcount;
+			pa.gbase = dtile + (long long)(y - gcount) * dst.stride;
+			__syncthreads();           // the group's intermediate rows are complete
+			pass2<C, DEEP>(pa);
+			__syncthreads();           // pass 1 may overwrite the intermediate rows again
+			gcount = 0;
+		}
+	}
+
+	// Never leave with a TMA load still in flight: wait for every stage that was issued.
+	for (int k = rs.stage + 1; k < rs.nstages && k < rs.stage + NS; ++k) {
+		if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
+		fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
+	}
+}
+
+struct DownLaunch {
+	const CUtensorMap *map;
+	const DevBatch *dst;
+	const FastTables *t;
+	const VTable *vt;
+	DownArgs da;
+	int n, channels, smem_bytes, bands;
+	cudaStream_t stream;
+};
+
+template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
+	auto kern = resize_down_kernel<DEPTH, DEEP, C>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+	if (e != cudaSuccess) return e;
+	dim3 grid((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
+	kern<<<grid, NT, a.smem_bytes, a.stream>>>(*a.map, *a.dst, *a.t, *a.vt, a.da);
+	return cudaGetLastError();
+}
+
+template <bool DEEP, int C> cudaError_t launch_depth(const DownLaunch &a) {
+	const int d = a.t->depth;
+	if (d <= 3) return launch_one<3, DEEP, C>(a);
+	if (d <= 4) return launch_one<4, DEEP, C>(a);
+	if (d <= 5) return launch_one<5, DEEP, C>(a);
+	if (d <= 6) return launch_one<6, DEEP, C>(a);
+	if (d <= 8) return launch_one<8, DEEP, C>(a);
+	return cudaErrorNotSupported;
+}
+
+}  // namespace down
+
+using down::DownLaunch;
+
+// One definition per instantiation unit (channels 1..4, 8- and 16-bit).
+template <bool DEEP, int C> cudaError_t launch_down(const DownLaunch &a);
+
+}  // namespace picha_b200
+#endif

@@ -33,7 +33,9 @@
 // other (DESIGN.md has the arithmetic).
 #include <algorithm>
 
-#include "resize_fast.cuh"
+#include <cmath>
+
+#include "resize_down.cuh"
 #include "tables.h"
 
 namespace picha_b200 {
@@ -115,8 +117,24 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	if (n > 65535) return cudaErrorNotSupported;
 	EncodeTiledFn encode = encode_fn();
 	if (!encode) return cudaErrorNotSupported;
-	const SmemLayout L = smem_layout(deep, t.tile_w, bpp, t.xstride);
-	if (L.total > max_dynamic_smem()) return cudaErrorNotSupported;
+	// Downscales whose accumulator ring is at most 8 deep take the kernel of resize_down.cuh.
+	bool use_down = fy.variant == FastAxisY::kDown && depth <= down::kMaxDepth;
+	DownLaunch dl;
+	if (use_down) {
+		float wmax = 0;
+		for (float w : fy.wv) wmax = std::fmax(wmax, std::fabs(w));
+		if (!(wmax < 128.0f)) use_down = false;      // weights carry 2^120 in that kernel
+		dl.da.nb = (t.xtaps + 3) / 4;
+		// few distinct weight rows (integer and small p/q ratios): the tile keeps just those
+		dl.da.uniq = t.xunique > 0 && t.xunique * 2 <= t.tile_w;
+		dl.da.wrows = dl.da.uniq ? t.xunique : t.tile_w;
+		dl.da.xscale = std::ldexp(1.0f, 149 - down::kVExp) / (deep ? 65535.0f : 255.0f);
+		dl.da.direct = (bpp == 4 || bpp == 8) &&
+		               ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (bpp - 1)) == 0;
+	}
+	const int smem_total = use_down ? down::smem_layout(t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
+	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
+	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;
 
 	// The batch as a 3-D tensor of 32-bit words: (words per row, rows, images).
 	CUtensorMap map;
@@ -137,8 +155,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// tables fit a launch's parameter block.
 	const int WS = (depth + 3) & ~3;
 	const int dh = dst.height;
+	const int ctas_per_sm = use_down ? 5 : 4;
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
-	long long want = (148LL * 4 * 16 + tiles - 1) / tiles;
+	long long want = (148LL * ctas_per_sm * 16 + tiles - 1) / tiles;
 	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
 	if (want > max_bands) want = max_bands;
 	if (want < 1) want = 1;
@@ -146,7 +165,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	auto band_fits = [&](int y0, int y1) {
 		const int rows = fy.cum[y1 - 1] - fy.smin[y0] + 1;
 		const int outs = fy.variant == 0 ? y1 - fy.ybase[fy.smin[y0]] : y1 - y0;
-		return outs <= kYtabMax && (fy.variant == 0 ? rows : outs) * WS <= kWtMax;
+		// (the downscaling kernel reads the weights one row ahead and may start up to depth - 1 outputs early)
+		return outs + kFastMaxDepth <= kYtabMax && ((fy.variant == 0 ? rows : outs) + 1) * WS <= kWtMax;
 	};
 	for (;;) {
 		bool ok = true;
@@ -159,9 +179,12 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	t.depth = depth;
 
 	FastLaunch a;
-	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = L.total; a.stream = stream;
+	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
 	VTable vt;
 	a.vt = &vt;
+	dl.map = &map; dl.dst = &dst; dl.t = &t; dl.vt = &vt; dl.n = n; dl.channels = channels; dl.smem_bytes = smem_total;
+	dl.stream = stream;
+	const float vscale = std::ldexp(1.0f, down::kVExp);
 	// Groups of consecutive bands whose tables fit one parameter block; one launch per group.
 	for (int yb = 0; yb < dh;) {
 		int ye = yb, bands = 0;
@@ -185,12 +208,33 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
 		// weight rows are re-strided from the host table's stride to the kernel's WS
 		const int first = fy.variant == 0 ? row_lo : yb, last = fy.variant == 0 ? row_hi : ye - 1;
-		for (int i = first; i <= last; ++i)
-			for (int j = 0; j < WS; ++j)
-				vt.wt[(i - first) * WS + j] = j < fy.stride ? fy.wv[(size_t)i * fy.stride + j] : 0.0f;
+		if (use_down) {
+			// slot order: the weight of row i for output y sits at y % depth; scaled by 2^kVExp
+			for (int i = first; i <= last; ++i) {
+				float *w = vt.wt + (i - first) * WS;
+				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
+				for (int j = 0; j < fy.depth; ++j) w[(fy.ybase[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale;
+			}
+		} else {
+			for (int i = first; i <= last; ++i)
+				for (int j = 0; j < WS; ++j)
+					vt.wt[(i - first) * WS + j] = j < fy.stride ? fy.wv[(size_t)i * fy.stride + j] : 0.0f;
+		}
 		a.bands = bands;
+		dl.bands = bands;
 		cudaError_t e;
-		if (fy.variant == 0) e = deep ? launch_fast_down_u16(a) : launch_fast_down_u8(a);
+		if (use_down) {
+			switch (channels * 2 + (deep ? 1 : 0)) {
+				case 2: e = launch_down<false, 1>(dl); break;
+				case 3: e = launch_down<true, 1>(dl); break;
+				case 4: e = launch_down<false, 2>(dl); break;
+				case 5: e = launch_down<true, 2>(dl); break;
+				case 6: e = launch_down<false, 3>(dl); break;
+				case 7: e = launch_down<true, 3>(dl); break;
+				case 8: e = launch_down<false, 4>(dl); break;
+				default: e = launch_down<true, 4>(dl); break;
+			}
+		} else if (fy.variant == 0) e = deep ? launch_fast_down_u16(a) : launch_fast_down_u8(a);
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;
 		*launches += 1;

@@ -2,6 +2,9 @@
 #include "tables.h"
 
 #include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
 
 namespace picha_b200 {
 namespace {
@@ -115,13 +118,26 @@ void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTab
 		}
 }
 
+// End taps the fast path leaves out: the reference keeps every tap whose weight is not exactly zero
+// (resize.cc:31-34), which at integer ratios includes end taps of ~1e-16 (sin(2*pi) in float).  A
+// tap below 2^-30 moves a result by < 1e-6 LSB -- far inside the fast path's +-1 LSB contract --
+// but costs a whole accumulator slot per thread in the vertical pass.
+static void pruned_range(const AxisTable &t, int i, int &k0, int &k1) {
+	const float eps = 9.3132257e-10f;   // 2^-30; the weights of an output sum to 1
+	k0 = 0;
+	k1 = t.count[i];
+	while (k1 - k0 > 1 && std::fabs(t.w[t.start[i] + k0]) < eps) ++k0;
+	while (k1 - k0 > 1 && std::fabs(t.w[t.start[i] + k1 - 1]) < eps) --k1;
+}
+
 void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 	f = FastAxisY();
 	const int n = t.dst_size;
-	std::vector<int> first(n), last(n);
+	std::vector<int> first(n), last(n), pk0(n), pk1(n);
 	for (int y = 0; y < n; ++y) {
+		pruned_range(t, y, pk0[y], pk1[y]);
 		int lo = t.src_size, hi = -1;
-		for (int k = 0; k < t.count[y]; ++k) {
+		for (int k = pk0[y]; k < pk1[y]; ++k) {
 			int r = t.eff[t.start[y] + k];
 			if (r < lo) lo = r;
 			if (r > hi) hi = r;
@@ -143,7 +159,7 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 	}
 	int need_down = 0, need_up = 0;
 	for (int y = 0; y < n; ++y) {
-		for (int k = 0; k < t.count[y]; ++k) {
+		for (int k = pk0[y]; k < pk1[y]; ++k) {
 			int d = y - f.ybase[t.eff[t.start[y] + k]] + 1;
 			if (d > need_down) need_down = d;
 		}
@@ -161,14 +177,14 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 		// 8 extra zero rows: the kernel copies the weights of whole 8-row stages
 		f.wv.assign(size_t(t.src_size + 8) * f.stride, 0.0f);
 		for (int y = 0; y < n; ++y)
-			for (int k = 0; k < t.count[y]; ++k) {
+			for (int k = pk0[y]; k < pk1[y]; ++k) {
 				int r = t.eff[t.start[y] + k];
 				f.wv[size_t(r) * f.stride + (y - f.ybase[r])] += t.w[t.start[y] + k];
 			}
 	} else {
 		f.wv.assign(size_t(n) * f.stride, 0.0f);
 		for (int y = 0; y < n; ++y)
-			for (int k = 0; k < t.count[y]; ++k) {
+			for (int k = pk0[y]; k < pk1[y]; ++k) {
 				int r = t.eff[t.start[y] + k];
 				f.wv[size_t(y) * f.stride + (r - f.lo[y])] += t.w[t.start[y] + k];
 			}
@@ -177,12 +193,36 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 
 void build_fast_x(const AxisTable &t, FastAxisX &f) {
 	f = FastAxisX();
-	f.taps = t.max_taps;
-	f.stride = (t.max_taps + 3) & ~3;      // float4 reads; 4 mod 8 keeps 8 neighbouring rows in distinct banks
+	f.first.resize(t.dst_size);
+	f.count.resize(t.dst_size);
+	std::vector<int> k0(t.dst_size);
+	for (int x = 0; x < t.dst_size; ++x) {
+		int k1;
+		pruned_range(t, x, k0[x], k1);
+		f.first[x] = t.first[x] + k0[x];
+		f.count[x] = k1 - k0[x];
+		if (f.count[x] > f.taps) f.taps = f.count[x];
+	}
+	f.stride = (f.taps + 3) & ~3;          // float4 reads; 4 mod 8 keeps 8 neighbouring rows in distinct banks
 	if (f.stride % 8 == 0) f.stride += 4;
 	f.w.assign(size_t(t.dst_size) * f.stride, 0.0f);
 	for (int x = 0; x < t.dst_size; ++x)
-		for (int k = 0; k < t.count[x]; ++k) f.w[size_t(x) * f.stride + k] = t.w[t.start[x] + k];
+		for (int k = 0; k < f.count[x]; ++k) f.w[size_t(x) * f.stride + k] = t.w[t.start[x] + k0[x] + k];
+	// unique rows (the padded rows compare equal exactly when counts and weights do: padding is zero and
+	// a pruned row never ends in an exact zero unless it is a single tap)
+	f.urow.resize(t.dst_size);
+	std::map<std::vector<uint32_t>, int> seen;
+	std::vector<uint32_t> key(f.stride + 1);
+	for (int x = 0; x < t.dst_size; ++x) {
+		key[0] = (uint32_t)f.count[x];
+		memcpy(&key[1], &f.w[size_t(x) * f.stride], f.stride * sizeof(float));
+		auto it = seen.find(key);
+		if (it == seen.end()) {
+			it = seen.emplace(key, f.unique++).first;
+			f.uw.insert(f.uw.end(), f.w.begin() + size_t(x) * f.stride, f.w.begin() + size_t(x + 1) * f.stride);
+		}
+		f.urow[x] = it->second;
+	}
 }
 
 }  // namespace picha_b200

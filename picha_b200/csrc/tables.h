@@ -62,7 +62,14 @@ void build_fast_y(const AxisTable &y, int max_depth, FastAxisY &out);
 struct FastAxisX {
 	int taps = 0;            // max taps of any output column
 	int stride = 0;          // row length >= taps: a multiple of 4 that is 4 mod 8
+	std::vector<int> first, count;   // [dst] tap range without end taps below 2^-30 (see tables.cc)
 	std::vector<float> w;    // [dst][stride]
+	// The same rows with duplicates removed (bitwise equal tap counts and weights: every column of an
+	// integer-ratio resize away from the edges, every q-th column of a p/q ratio): the downscaling
+	// kernel keeps only these in shared memory when there are few of them.
+	std::vector<int> urow;   // [dst] index of the column's row in uw
+	std::vector<float> uw;   // [unique][stride]
+	int unique = 0;
 };
 void build_fast_x(const AxisTable &x, FastAxisX &out);
 

@@ -2,7 +2,7 @@
 # A/B kernel variants on the GPU box: tools/ab.sh lib1.so lib2.so ...   ("default" = in-tree build)
 for lib in "$@"; do
   if [ "$lib" = default ]; then unset PICHA_B200_LIB; else export PICHA_B200_LIB=$lib; fi
-  for w in cfg3 cfg5 cfg4; do
+  for w in ${WORKLOADS:-cfg3 cfg5 cfg4}; do
     timeout 120 python bench.py --workload $w --also none --no-cpu --no-e2e --steps 5 --warmup 3 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:

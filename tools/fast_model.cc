@@ -44,7 +44,7 @@ extern "C" int fast_model(int tag, float width, const uint8_t *src, int sstride,
 	const int bpp = channels * (deep ? 2 : 1);
 	int unit = 16;
 	while (unit > 1 && (unit / 2 * bpp) % 16 == 0) unit /= 2;
-	const int tile_w = fy.variant < 0 ? 0 : fast_tile_width_model(ax.first.data(), ax.count.data(), dw, channels, unit, 256);
+	const int tile_w = fy.variant < 0 ? 0 : fast_tile_width_model(fx.first.data(), fx.count.data(), dw, channels, unit, 256);
 	info[0] = fy.variant; info[1] = fy.depth; info[2] = tile_w; info[3] = 0; info[4] = fx.taps; info[5] = band_h;
 	if (fy.variant < 0 || tile_w == 0) return 1;
 	(void)force_variant;
@@ -63,7 +63,7 @@ extern "C" int fast_model(int tag, float width, const uint8_t *src, int sstride,
 		const int y1 = y0 + band_h < dh ? y0 + band_h : dh;
 		for (int x0 = 0; x0 < dw; x0 += tile_w) {
 			const int tw = x0 + tile_w < dw ? tile_w : dw - x0;
-			const int sx0 = ax.first[x0] / unit * unit;
+			const int sx0 = fx.first[x0] / unit * unit;
 			const int v0 = sx0 * channels;   // first value of the tile row
 			const int rlo = fy.smin[y0], rhi = fy.cum[y1 - 1];
 			if (rlo < 0 || rhi >= sh || rlo > rhi) { ++bad; continue; }
@@ -74,22 +74,23 @@ extern "C" int fast_model(int tag, float width, const uint8_t *src, int sstride,
 				std::vector<std::vector<float>> acc(D, std::vector<float>(row_values, 0.0f));
 				int r = rlo, y = fy.ybase[rlo];
 				if (y > y0) ++bad;
-				int s = 0;
+				// fixed slots, as in csrc/resize_down.cuh: output y accumulates in slot y % D and the
+				// weights of a source row are laid out in slot order
 				while (y < y1) {
 					const int need = fy.cum[y];
 					for (; r <= need; ++r) {
 						if (r > rhi) ++bad;
 						++consumed;
-						for (int j = 0; j < D; ++j) {
-							const float w = fy.wv[(size_t)r * fy.stride + j];
-							for (int i = 0; i < row_values; ++i)
-								acc[(s + j) % D][i] = std::fmaf(w, value(r, v0 + i), acc[(s + j) % D][i]);
-						}
+						std::vector<float> ws(D, 0.0f);
+						for (int j = 0; j < D; ++j) ws[(fy.ybase[r] + j) % D] = fy.wv[(size_t)r * fy.stride + j];
+						if (fy.ybase[r] > y) ++bad;            // row r only feeds outputs y .. y + D - 1
+						for (int j = 0; j < D; ++j)
+							for (int i = 0; i < row_values; ++i) acc[j][i] = std::fmaf(ws[j], value(r, v0 + i), acc[j][i]);
 					}
+					const int s = y % D;
 					if (y >= y0) tmp[y - y0] = acc[s];
 					std::fill(acc[s].begin(), acc[s].end(), 0.0f);
 					++y;
-					s = (s + 1) % D;
 				}
 				if (consumed != rhi - rlo + 1) ++bad;
 			} else {
@@ -126,7 +127,7 @@ extern "C" int fast_model(int tag, float width, const uint8_t *src, int sstride,
 			}
 			for (int y = y0; y < y1; ++y)
 				for (int xx = 0; xx < tw; ++xx) {
-					const int x = x0 + xx, first = ax.first[x] - sx0, cnt = ax.count[x];
+					const int x = x0 + xx, first = fx.first[x] - sx0, cnt = fx.count[x];
 					if (first < 0 || (first + cnt) * channels > row_values) { ++bad; continue; }
 					for (int ch = 0; ch < channels; ++ch) {
 						float a = 0.0f;
