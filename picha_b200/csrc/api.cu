@@ -91,6 +91,7 @@ struct Plan {
 	ResizeTables t{};
 	FastTables ft{};            // tile_w / band_h are filled per launch
 	FastAxisY fy;               // vertical axis of the fast path (host; sliced into kernel parameters)
+	FastAxisX fx;               // horizontal axis of the fast path (host copy, for launch planning)
 	int fast_tile_w[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
 	~Plan() { if (blob) cudaFree(blob); }
 };
@@ -238,11 +239,17 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 
 	// fast path tables (vertical axis as accumulator ring / row window, horizontal axis padded)
 	FastAxisY &fy = p->fy;
-	FastAxisX fx;
+	FastAxisX &fx = p->fx;
 	build_fast_y(p->y, kFastMaxDepth, fy);
 	build_fast_x(p->x, fx);
 	size_t o_fxw = put_f(fx.w), o_fxfirst = put_i(fx.first), o_fxcount = put_i(fx.count);
 	size_t o_fxrow = put_i(fx.urow), o_fxuw = put_f(fx.uw);
+	FlatRows flat[2];
+	size_t o_ecol[2], o_esrc[2], o_eoff[2];
+	for (int ci = 0; ci < 2; ++ci) {
+		build_flat_rows(fx, ci ? 3 : 1, flat[ci]);
+		o_ecol[ci] = put_i(flat[ci].col); o_esrc[ci] = put_i(flat[ci].src); o_eoff[ci] = put_i(flat[ci].off);
+	}
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
 		// Tile widths: multiples of the 16-byte pixel group when the destination is the big side (vector
@@ -267,7 +274,12 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->ft.xfirst = ib + o_fxfirst; p->ft.xcount = ib + o_fxcount;
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
 	p->ft.xtaps = fx.taps;
+	p->ft.h_xfirst = fx.first.data(); p->ft.h_xcount = fx.count.data(); p->ft.h_xw = fx.w.data();
 	p->ft.xrow = ib + o_fxrow; p->ft.xuw = fb + o_fxuw; p->ft.xunique = fx.unique;
+	for (int ci = 0; ci < 2; ++ci) {
+		p->ft.xe_col[ci] = ib + o_ecol[ci]; p->ft.xe_src[ci] = ib + o_esrc[ci]; p->ft.xe_off[ci] = ib + o_eoff[ci];
+		p->ft.xe_count[ci] = (int)flat[ci].src.size();
+	}
 	p->ft.xshort = fx.taps <= 4 ? 4 : (fx.taps <= 8 ? 8 : 0);
 
 	dev->plans[key] = p;

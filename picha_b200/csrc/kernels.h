@@ -49,6 +49,12 @@ struct FastTables {
 	const int *xrow;     // [dst] the column's row in xuw
 	const float *xuw;    // [xunique][xstride] distinct weight rows
 	int xunique;
+	// flat form for 1 ([0]) and 3 ([1]) channels (tables.h: FlatRows)
+	const int *xe_col[2], *xe_src[2], *xe_off[2];
+	int xe_count[2];
+	// host copies of xfirst / xcount / xw (launch planning; never dereferenced on the device)
+	const int *h_xfirst, *h_xcount;
+	const float *h_xw;
 	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA

@@ -40,8 +40,18 @@ constexpr int NT = 64;             // threads per CTA
 constexpr int NV = 16;             // channel values of one source row owned by a thread
 constexpr int ROWV = NT * NV;      // values per staged row (the tile geometry of the generic kernel)
 static_assert(ROWV == fast::NT * fast::NV, "tile widths are planned once for both kernels");
-constexpr int G = 4;               // output rows per pass-2 group
-constexpr int TMPS = ROWV + 4;     // floats per intermediate row (+4: rows land 4 banks apart)
+// Output rows per pass-2 group: 4 or 8 (template parameter GR).  With 8, the eight lanes that share a
+// shared-memory phase of a float4 read are the eight rows of ONE column -- conflict-free whatever
+// the ratio; with 4 they are four rows of two neighbouring columns, which is conflict-free only when
+// the columns' windows start the right distance apart (e.g. 4:1 rgba) but costs half the memory.
+#ifndef PICHA_DOWN_ODD_PAD
+#define PICHA_DOWN_ODD_PAD 8
+#endif
+// floats per intermediate row: the rows of a group land 4 banks apart (8 for odd channel counts, whose
+// neighbouring columns start 20 or 24 floats apart at a 7.5:1 ratio)
+__host__ __device__ constexpr int tmps(int channels, int group) {
+	return ROWV + (group == 4 && (channels & 1) ? PICHA_DOWN_ODD_PAD : 4);
+}
 #ifndef PICHA_DOWN_NS
 #define PICHA_DOWN_NS 2
 #endif
@@ -52,24 +62,29 @@ constexpr int kMaxDepth = 8;
 
 __host__ __device__ constexpr int stage_rows(bool deep) { return deep ? 4 : 8; }
 
+// Odd channel counts: float4 chunks of an expanded weight row, (nb + 1) blocks of `channels` chunks.
+__host__ __device__ constexpr int flat_chunks(int channels, int nb) { return channels * (nb + 1); }
+
 struct SmemLayout {
 	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, bars, total;
 };
 
 // nb: blocks of 4 horizontal taps; wrows: weight rows held in shared memory (the plan's distinct
 // rows, or one per column of the tile); direct: pixels go straight to global memory (no output tile).
-__host__ __device__ inline SmemLayout smem_layout(int tile_w, int bpp, int channels, int nb, int wrows, bool direct) {
+__host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct) {
 	SmemLayout L;
 	L.ring = 0;
 	L.tmp = L.ring + NS * STAGE_BYTES;
 	// Every column runs the same nb blocks of taps; a column with a shorter window (image edges) reads on
 	// behind it with zero weights -- into the next row of the group or, from the last row, into this
 	// zeroed tail (at most 4 * nb pixels).
-	L.tmp_floats = G * TMPS + (4 * nb * channels + 63) / 64 * 64;
+	L.tmp_floats = G * tmps(channels, G) + (4 * nb * channels + 16 + 63) / 64 * 64;
 	L.out = L.tmp + L.tmp_floats * 4;
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + (direct ? 0 : G * L.out_stride);
-	L.xs2 = 8 * nb + 4;                    // floats per column: duplicated weights, rows 4 banks apart
+	// floats per weight row, an odd number of float4s (rows spread over the banks): duplicated weights
+	// for even channel counts, the expanded flat form (see PixelAcc<3>) for odd ones
+	L.xs2 = 4 * (((channels & 1) ? flat_chunks(channels, nb) : 2 * nb) | 1);
 	L.xf = L.xw + wrows * L.xs2 * 4;         // per column: {byte offset of the first tap in a row, of the weight row}
 	L.bars = L.xf + tile_w * 8;
 	L.total = L.bars + 2 * NS * 8;
@@ -132,10 +147,15 @@ __device__ __forceinline__ RingState ring_advance(const CUtensorMap *map, uint32
 	if (rs.stage >= 0 && rs.stage + NS < rs.nstages) {
 		__syncwarp();
 		if ((tid & 31) == 0) {
-			uint32_t old;
-			asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(bars + 8 * (NS + prev)) : "memory");
-			if (old == NT / 32 - 1) {
-				asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 8 * (NS + prev)), "r"(0) : "memory");
+			// arrive on the stage's hand-back barrier; the state it returns holds the pending count before
+			// this arrival: 1 means every other warp has been here already
+			uint32_t pending;
+			asm volatile(
+				"{\n\t.reg .b64 st;\n\t"
+				"mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
+				"mbarrier.pending_count.b64 %0, st;\n\t}"
+				: "=r"(pending) : "r"(bars + 8 * (NS + prev)) : "memory");
+			if (pending == 1) {
 				fast::mbar_expect_tx_a(bars + 8 * prev, STAGE_BYTES);
 #pragma unroll
 				for (int b = 0; b < BOXES; ++b)
@@ -195,7 +215,7 @@ template <> struct PixelAcc<4> {
 		ffma2(a01, p4, w2); ffma2(a23, p5, w2);
 		ffma2(a01, p6, w3); ffma2(a23, p7, w3);
 	}
-	__device__ __forceinline__ void result(float *f) const { unpair(a01, f[0], f[1]); unpair(a23, f[2], f[3]); }
+	__device__ __forceinline__ void result(float *f, int) const { unpair(a01, f[0], f[1]); unpair(a23, f[2], f[3]); }
 };
 template <> struct PixelAcc<2> {
 	u64 e = 0, od = 0;
@@ -207,7 +227,7 @@ template <> struct PixelAcc<2> {
 		ffma2(e, p0, w0); ffma2(od, p1, w1);
 		ffma2(e, p2, w2); ffma2(od, p3, w3);
 	}
-	__device__ __forceinline__ void result(float *f) const {
+	__device__ __forceinline__ void result(float *f, int) const {
 		float e0, e1, o0, o1;
 		unpair(e, e0, e1);
 		unpair(od, o0, o1);
@@ -215,46 +235,51 @@ template <> struct PixelAcc<2> {
 		f[1] = e1 + o1;
 	}
 };
+// Odd channel counts read the row as a flat float array in aligned float4 chunks, against a weight
+// row expanded to one weight per float (each tap `C` times) and shifted by the window's misalignment
+// `off`.  Float j of the window belongs to channel (j - off) mod C.  For C = 3 a block is three
+// chunks (12 floats, a multiple of 3): the pairs (j, j+1) of a block always fall on the residue pairs
+// (0,1) (2,0) (1,2) (0,1) (2,0) (1,2), so three packed accumulators suffice.
 template <> struct PixelAcc<3> {
-	u64 a01 = 0, b01 = 0;
-	float a2 = 0.0f, b2 = 0.0f;
+	u64 p01 = 0, p20 = 0, p12 = 0;
 	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
-		u64 w0, w1, w2, w3;
+		u64 w0, w1, w2, w3, w4, w5, f0, f1, f2, f3, f4, f5;
 		lds_2x64(w, w0, w1);
 		lds_2x64(w + 16, w2, w3);
-		float s0, s1, s2, s3, d;
-		unpair(w0, s0, d); unpair(w1, s1, d); unpair(w2, s2, d); unpair(w3, s3, d);
-		float q[12];
-#pragma unroll
-		for (int i = 0; i < 12; ++i) q[i] = lds<float>(v + 4 * i);
-		ffma2(a01, pair(q[0], q[1]), w0); a2 = fmaf(s0, q[2], a2);
-		ffma2(b01, pair(q[3], q[4]), w1); b2 = fmaf(s1, q[5], b2);
-		ffma2(a01, pair(q[6], q[7]), w2); a2 = fmaf(s2, q[8], a2);
-		ffma2(b01, pair(q[9], q[10]), w3); b2 = fmaf(s3, q[11], b2);
+		lds_2x64(w + 32, w4, w5);
+		lds_2x64(v, f0, f1);
+		lds_2x64(v + 16, f2, f3);
+		lds_2x64(v + 32, f4, f5);
+		ffma2(p01, f0, w0); ffma2(p20, f1, w1); ffma2(p12, f2, w2);
+		ffma2(p01, f3, w3); ffma2(p20, f4, w4); ffma2(p12, f5, w5);
 	}
-	__device__ __forceinline__ void result(float *f) const {
-		float x0, x1, y0, y1;
-		unpair(a01, x0, x1);
-		unpair(b01, y0, y1);
-		f[0] = x0 + y0;
-		f[1] = x1 + y1;
-		f[2] = a2 + b2;
+	__device__ __forceinline__ void result(float *f, int off) const {
+		float a, b, c, d, e, g;
+		unpair(p01, a, b);
+		unpair(p20, c, d);
+		unpair(p12, e, g);
+		const float r0 = a + d, r1 = b + e, r2 = c + g;   // sums over the floats with j mod 3 = 0, 1, 2
+		const int o = off == 3 ? 0 : off;                 // channel c sits at residue (c + off) mod 3
+		f[0] = o == 0 ? r0 : o == 1 ? r1 : r2;
+		f[1] = o == 0 ? r1 : o == 1 ? r2 : r0;
+		f[2] = o == 0 ? r2 : o == 1 ? r0 : r1;
 	}
 };
 template <> struct PixelAcc<1> {
-	float e = 0.0f, od = 0.0f;
+	u64 p = 0, q = 0;
 	__device__ __forceinline__ void block(uint32_t w, uint32_t v) {
-		u64 w0, w1, w2, w3;
+		u64 w0, w1, f0, f1;
 		lds_2x64(w, w0, w1);
-		lds_2x64(w + 16, w2, w3);
-		float s0, s1, s2, s3, d;
-		unpair(w0, s0, d); unpair(w1, s1, d); unpair(w2, s2, d); unpair(w3, s3, d);
-		e = fmaf(s0, lds<float>(v), e);
-		od = fmaf(s1, lds<float>(v + 4), od);
-		e = fmaf(s2, lds<float>(v + 8), e);
-		od = fmaf(s3, lds<float>(v + 12), od);
+		lds_2x64(v, f0, f1);
+		ffma2(p, f0, w0);
+		ffma2(q, f1, w1);
 	}
-	__device__ __forceinline__ void result(float *f) const { f[0] = e + od; }
+	__device__ __forceinline__ void result(float *f, int) const {
+		float a, b, c, d;
+		unpair(p, a, b);
+		unpair(q, c, d);
+		f[0] = (a + b) + (c + d);
+	}
 };
 
 // A thread produces P2U output pixels at a time (same row of the group, columns 16 apart): their
@@ -264,15 +289,16 @@ template <> struct PixelAcc<1> {
 #ifndef PICHA_DOWN_P2U
 #define PICHA_DOWN_P2U 4
 #endif
-template <int C, bool DEEP>
+template <int C, bool DEEP, int GR>
 __device__ __noinline__ void pass2(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	constexpr int U = PICHA_DOWN_P2U;
-	const int total = a.tw * 4;
-	const int g = a.tid & 3;                       // NT is a multiple of 4: the same row for every item
-	const uint32_t vrow = a.sbase + a.tmp + 4 * g * TMPS;
+	constexpr int GSH = GR == 8 ? 3 : 2;
+	const int total = a.tw * GR;
+	const int g = a.tid & (GR - 1);                // NT is a multiple of GR: the same row for every item
+	const uint32_t vrow = a.sbase + a.tmp + 4 * g * tmps(C, GR);
 	for (int o0 = a.tid; o0 < total; o0 += U * NT) {
-		int xx[U];
+		int xx[U], off[U];
 		bool live[U];
 		uint32_t w[U], v[U];
 		PixelAcc<C> acc[U];
@@ -280,24 +306,27 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 		for (int u = 0; u < U; ++u) {
 			const int o = o0 + u * NT;
 			live[u] = o < total && g < a.ng;
-			xx[u] = live[u] ? o >> 2 : 0;            // idle slots recompute column 0 and store nothing
+			xx[u] = live[u] ? o >> GSH : 0;          // idle slots recompute column 0 and store nothing
 			const uint2 e = lds<uint2>(a.sbase + a.xf + 8 * xx[u]);
 			v[u] = vrow + e.x;
-			w[u] = a.sbase + a.xw + e.y;
+			w[u] = a.sbase + a.xw + (e.y & ~3u);
+			off[u] = e.y & 3;
 		}
-		for (int kb = 0; kb < a.nb; ++kb) {
+		constexpr int WSTEP = (C & 1) ? 16 * C : 32, VSTEP = 16 * C;   // bytes per block: 4 taps (even C), 4 * C floats (odd C)
+		const int blocks = (C & 1) ? a.nb + 1 : a.nb;
+		for (int kb = 0; kb < blocks; ++kb) {
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
 				acc[u].block(w[u], v[u]);
-				w[u] += 32;
-				v[u] += 16 * C;
+				w[u] += WSTEP;
+				v[u] += VSTEP;
 			}
 		}
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
 			if (!live[u]) continue;
 			float f[C];
-			acc[u].result(f);
+			acc[u].result(f, off[u]);
 			if ((BPP == 4 || BPP == 8) && a.direct) {
 				uint32_t pv[C];
 #pragma unroll
@@ -324,7 +353,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 #define PICHA_DOWN_MINB(D) ((D) <= 4 ? 6 : (D) <= 6 ? 5 : 4)
 #endif
 
-template <int DEPTH, bool DEEP, int C>
+template <int DEPTH, bool DEEP, int C, int GR>
 __global__ void __launch_bounds__(NT, PICHA_DOWN_MINB(DEPTH))
 resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, DownArgs da) {
@@ -333,6 +362,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
 	constexpr int WPT = DEEP ? 8 : 4;            // 32-bit words of a source row per thread
 	const int tid = threadIdx.x;
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_one
 
 	const int x0 = blockIdx.x * t.tile_w;
 	const int tw = min(t.tile_w, dst.width - x0);
@@ -343,10 +373,10 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
 
 	const bool direct = (BPP == 4 || BPP == 8) && da.direct;
-	const SmemLayout L = smem_layout(t.tile_w, BPP, C, da.nb, da.wrows, direct);
+	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
-	const uint32_t bars = sbase + L.bars;          // full[NS] mbarriers, then NS hand-back counters
+	const uint32_t bars = sbase + L.bars;          // full[NS] mbarriers, then NS hand-back mbarriers
 	const uint32_t ring = sbase + L.ring;
 
 	RingState rs;
@@ -356,7 +386,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	if (tid == 0) {
 		for (int i = 0; i < NS; ++i) {
 			mbar_init_a(bars + 8 * i, 1);
-			asm volatile("st.shared.u32 [%0], %1;" ::"r"(bars + 8 * (NS + i)), "r"(0) : "memory");   // hand-back counter
+			mbar_init_a(bars + 8 * (NS + i), NT / 32);   // hand-back: one arrival per warp
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -370,17 +400,31 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	}
 	// this tile's horizontal tables -> shared memory: weights scaled and duplicated (packed-FMA operands)
 	const bool uniq = da.uniq != 0;                // the plan's distinct rows, else one row per column
-	const float *wsrc = uniq ? t.xuw : t.xw + (long long)x0 * t.xstride;
 	const int wrows = uniq ? da.wrows : tw;
-	for (int i = tid; i < wrows * da.nb * 4; i += NT) {
-		const int row = i / (da.nb * 4), k = i - row * (da.nb * 4);
-		const float w = k < t.xstride ? wsrc[(long long)row * t.xstride + k] * da.xscale : 0.0f;
-		asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
+	if (C & 1) {
+		constexpr int ci = C == 3;
+		const int nfl = 4 * flat_chunks(C, da.nb);
+		for (int i = tid; i < wrows * nfl; i += NT) {
+			const int row = i / nfl, j = i - row * nfl;
+			const int src = uniq ? t.xe_src[ci][row] : t.xrow[x0 + row];
+			const int off = uniq ? t.xe_off[ci][row] : ((t.xfirst[x0 + row] - sx0) * C) & 3;
+			const int k = j - off, kk = k / C;
+			const float w = k >= 0 && kk < t.xstride ? t.xuw[(long long)src * t.xstride + kk] * da.xscale : 0.0f;
+			sts(sbase + L.xw + 4 * (row * L.xs2 + j), w);
+		}
+	} else {
+		const float *wsrc = uniq ? t.xuw : t.xw + (long long)x0 * t.xstride;
+		for (int i = tid; i < wrows * da.nb * 4; i += NT) {
+			const int row = i / (da.nb * 4), k = i - row * (da.nb * 4);
+			const float w = k < t.xstride ? wsrc[(long long)row * t.xstride + k] * da.xscale : 0.0f;
+			asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
+		}
 	}
 	for (int i = tid; i < tw; i += NT) {
-		const int first = (t.xfirst[x0 + i] - sx0) * C * 4;    // byte offset of the column's first tap in a row
-		const int wrow = uniq ? t.xrow[x0 + i] : i;
-		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"(first), "r"(wrow * L.xs2 * 4) : "memory");
+		// {byte offset of the column's first (aligned) float in a row, byte offset of its weight row | misalignment}
+		const int first = (t.xfirst[x0 + i] - sx0) * C, off = (C & 1) ? first & 3 : 0;
+		const int wrow = !uniq ? i : (C & 1) ? t.xe_col[C == 3][x0 + i] : t.xrow[x0 + i];
+		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"((first - off) * 4), "r"(wrow * L.xs2 * 4 + off) : "memory");
 	}
 	// padded taps multiply whatever lies behind a column's window by zero: make sure that is never a NaN
 	for (int i = tid; i < L.tmp_floats; i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
@@ -489,11 +533,11 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 				if (y >= y0) {
 #if PICHA_DOWN_EMIT_SCALAR
 #pragma unroll
-					for (int i = 0; i < NV; ++i) sts(my_tmp + gcount * (TMPS * 4) + (i >> 2) * 1024 + (i & 3) * 4, acc[j][i]);
+					for (int i = 0; i < NV; ++i) sts(my_tmp + gcount * (tmps(C, GR) * 4) + (i >> 2) * 1024 + (i & 3) * 4, acc[j][i]);
 #else
 #pragma unroll
 					for (int q = 0; q < 4; ++q)
-						sts(my_tmp + gcount * (TMPS * 4) + q * 1024,
+						sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024,
 						    make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]));
 #endif
 					++gcount;
@@ -506,11 +550,11 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		}
 		++y;
 		if (++yslot == DEPTH) yslot = 0;
-		if (gcount == G || (y == y1 && gcount > 0)) {
+		if (gcount == GR || (y == y1 && gcount > 0)) {
 			pa.ng = gcount;
 			pa.gbase = dtile + (long long)(y - gcount) * dst.stride;
 			__syncthreads();           // the group's intermediate rows are complete
-			pass2<C, DEEP>(pa);
+			pass2<C, DEEP, GR>(pa);
 			__syncthreads();           // pass 1 may overwrite the intermediate rows again
 			gcount = 0;
 		}
@@ -521,6 +565,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
 		fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
 	}
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 struct DownLaunch {
@@ -530,16 +575,36 @@ struct DownLaunch {
 	const VTable *vt;
 	DownArgs da;
 	int n, channels, smem_bytes, bands;
+	int overlap;    // not the first launch of this resize: may start while the previous one drains
+	int group;      // output rows per pass-2 group (4 or 8)
 	cudaStream_t stream;
 };
 
-template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
-	auto kern = resize_down_kernel<DEPTH, DEEP, C>;
+// The launches of one resize (one per group of row bands) write disjoint rows and read the same
+// source, so nothing orders them: from the second on they are launched with programmatic stream
+// serialization and start filling SMs as soon as every CTA of the previous launch has started
+// (griddepcontrol.launch_dependents at the top of the kernel) -- the partial last wave of each
+// launch would otherwise idle a good part of the GPU.  Every CTA ends with griddepcontrol.wait, so a
+// launch never completes before its predecessor and whatever follows in the stream sees all of them.
+template <int DEPTH, bool DEEP, int C, int GR> cudaError_t launch_group(const DownLaunch &a) {
+	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
 	if (e != cudaSuccess) return e;
-	dim3 grid((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
-	kern<<<grid, NT, a.smem_bytes, a.stream>>>(*a.map, *a.dst, *a.t, *a.vt, a.da);
-	return cudaGetLastError();
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
+	cfg.blockDim = dim3(NT);
+	cfg.dynamicSmemBytes = a.smem_bytes;
+	cfg.stream = a.stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = a.overlap ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kern, *a.map, *a.dst, *a.t, *a.vt, a.da);
+}
+
+template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
+	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8>(a) : launch_group<DEPTH, DEEP, C, 4>(a);
 }
 
 template <bool DEEP, int C> cudaError_t launch_depth(const DownLaunch &a) {

@@ -34,8 +34,9 @@
 #include <algorithm>
 
 #include <cmath>
+#include <cstdlib>
 
-#include "resize_down.cuh"
+#include "resize_up.cuh"
 #include "tables.h"
 
 namespace picha_b200 {
@@ -126,13 +127,49 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		if (!(wmax < 128.0f)) use_down = false;      // weights carry 2^120 in that kernel
 		dl.da.nb = (t.xtaps + 3) / 4;
 		// few distinct weight rows (integer and small p/q ratios): the tile keeps just those
-		dl.da.uniq = t.xunique > 0 && t.xunique * 2 <= t.tile_w;
-		dl.da.wrows = dl.da.uniq ? t.xunique : t.tile_w;
+		const int rows = (channels & 1) ? t.xe_count[channels == 3] : t.xunique;
+		dl.da.uniq = rows > 0 && rows * 2 <= t.tile_w;
+		dl.da.wrows = dl.da.uniq ? rows : t.tile_w;
 		dl.da.xscale = std::ldexp(1.0f, 149 - down::kVExp) / (deep ? 65535.0f : 255.0f);
 		dl.da.direct = (bpp == 4 || bpp == 8) &&
 		               ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (bpp - 1)) == 0;
 	}
-	const int smem_total = use_down ? down::smem_layout(t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
+	// 4-channel upscales with a shallow row window take the kernel of resize_up.cuh.
+	bool use_up = fy.variant == FastAxisY::kUp && channels == 4 && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
+	              ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)(n > 1 ? dst.step : 0)) & 15) == 0;
+	UpLaunch ul;
+	const int *host_xfirst = t.h_xfirst, *host_xcount = t.h_xcount;
+	const float *host_xw = t.h_xw;
+	if (use_up) {
+		// per tile: bytes of a source row to stage; per thread (4 output pixels): source pixels touched
+		int win_px = 0, wpx = 0;
+		for (int x0 = 0; x0 < dst.width; x0 += up::TILE) {
+			const int x1 = std::min(dst.width, x0 + up::TILE);
+			const int sx0 = host_xfirst[x0] / t.align_px * t.align_px;
+			for (int x = x0; x < x1; ++x) win_px = std::max(win_px, host_xfirst[x] + host_xcount[x] - sx0);
+			for (int g0 = x0; g0 < x1; g0 += up::NPX) {
+				int lo = host_xfirst[g0], hi = 0;
+				for (int x = g0; x < std::min(x1, g0 + up::NPX); ++x) {
+					lo = std::min(lo, host_xfirst[x]);
+					hi = std::max(hi, host_xfirst[x] + host_xcount[x]);
+				}
+				if (lo != host_xfirst[g0]) use_up = false;       // the window is anchored at the group's first column
+				wpx = std::max(wpx, hi - lo);
+			}
+		}
+		float wmax = 0;
+		for (int i = 0; i < dst.width * t.xstride; ++i) wmax = std::fmax(wmax, std::fabs(host_xw[i]));
+		if (wpx > 8 || !(wmax < 128.0f)) use_up = false;
+		ul.wpx = wpx;
+		ul.ua.win_bytes = (win_px * bpp + 15) & ~15;
+		ul.ua.hscale = std::ldexp(1.0f, up::kHExp);
+		if (up::smem_bytes(ul.ua.win_bytes) > max_dynamic_smem()) use_up = false;
+	}
+	if (use_down) {
+		const char *g = getenv("PICHA_B200_DOWN_G");
+		dl.group = g ? atoi(g) == 8 ? 8 : 4 : 4;
+	}
+	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
 	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;
 
@@ -155,7 +192,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// tables fit a launch's parameter block.
 	const int WS = (depth + 3) & ~3;
 	const int dh = dst.height;
-	const int ctas_per_sm = use_down ? 5 : 4;
+	const int ctas_per_sm = use_down || use_up ? 6 : 4;
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
 	long long want = (148LL * ctas_per_sm * 16 + tiles - 1) / tiles;
 	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
@@ -185,6 +222,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	dl.map = &map; dl.dst = &dst; dl.t = &t; dl.vt = &vt; dl.n = n; dl.channels = channels; dl.smem_bytes = smem_total;
 	dl.stream = stream;
 	const float vscale = std::ldexp(1.0f, down::kVExp);
+	ul.src = &src; ul.dst = &dst; ul.t = &t; ul.vt = &vt; ul.n = n; ul.stream = stream;
+	const float vscale_up = std::ldexp(1.0f, 149 - up::kHExp) / (deep ? 65535.0f : 255.0f);
 	// Groups of consecutive bands whose tables fit one parameter block; one launch per group.
 	for (int yb = 0; yb < dh;) {
 		int ye = yb, bands = 0;
@@ -204,8 +243,10 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			vt.band_rhi[b] = fy.cum[y1 - 1];
 			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[fy.smin[y0]] : y0;
 		}
-		const int *ysrc = fy.variant == 0 ? fy.cum.data() : fy.lo.data();
+		const int *ysrc = fy.variant == 0 || use_up ? fy.cum.data() : fy.lo.data();
 		for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
+		// the new kernels look one output ahead; the upscaling kernel's output loop ends on this sentinel
+		vt.ytab[ye - vt.out_base] = use_up || ye >= dh ? -1 : ysrc[ye];
 		// weight rows are re-strided from the host table's stride to the kernel's WS
 		const int first = fy.variant == 0 ? row_lo : yb, last = fy.variant == 0 ? row_hi : ye - 1;
 		if (use_down) {
@@ -215,6 +256,13 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
 				for (int j = 0; j < fy.depth; ++j) w[(fy.ybase[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale;
 			}
+		} else if (use_up) {
+			// slot order: source row r sits in window slot r % depth; scaled so the result lands on [0, 1]
+			for (int i = first; i <= last; ++i) {
+				float *w = vt.wt + (i - first) * WS;
+				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
+				for (int j = 0; j < fy.depth; ++j) w[(fy.lo[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale_up;
+			}
 		} else {
 			for (int i = first; i <= last; ++i)
 				for (int j = 0; j < WS; ++j)
@@ -222,6 +270,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		}
 		a.bands = bands;
 		dl.bands = bands;
+		dl.overlap = yb > 0;
+		ul.bands = bands;
+		ul.overlap = yb > 0;
 		cudaError_t e;
 		if (use_down) {
 			switch (channels * 2 + (deep ? 1 : 0)) {
@@ -234,7 +285,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				case 8: e = launch_down<false, 4>(dl); break;
 				default: e = launch_down<true, 4>(dl); break;
 			}
-		} else if (fy.variant == 0) e = deep ? launch_fast_down_u16(a) : launch_fast_down_u8(a);
+		} else if (use_up) e = deep ? launch_up_u16(ul) : launch_up_u8(ul);
+		else if (fy.variant == 0) e = deep ? launch_fast_down_u16(a) : launch_fast_down_u8(a);
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;
 		*launches += 1;

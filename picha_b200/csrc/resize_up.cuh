@@ -1,0 +1,335 @@
+// Upscaling variant of the fast resize path for 4-channel pixels (rgba, r16g16b16a16); reference:
+// src/resize.cc:66-134.  Included by the resize_up_*.cu instantiation units.
+//
+// An upscale is the mirror image of a downscale: the expensive pass is the one that runs at the
+// OUTPUT resolution, so that is the pass that has to be thread-private.  Here that is the vertical
+// pass, and the order is the reference's own -- horizontal first:
+//   * A thread owns 4 consecutive output pixels (16 channel values) of the tile and keeps a window of
+//     DEPTH horizontally-filtered rows of them in registers (DEPTH x 16 floats).
+//   * Horizontal pass, once per SOURCE row: the thread reads the <= WPX source pixels its four
+//     outputs touch straight from the staged row (bytes as subnormal floats, see resize_down.cuh),
+//     and multiplies them with a dense 4 x WPX weight block it holds in registers (the block is the
+//     same for every row; entries outside a column's taps are zero).  No intermediate ever goes
+//     through shared memory and there is no CTA-wide barrier in the kernel.
+//   * Vertical pass, once per OUTPUT row: DEPTH FMAs per value with warp-uniform weights from the
+//     constant bank (laid out by window slot: row r lives in slot r % DEPTH, so the code is the same
+//     for every row), a saturating last FMA, two more instructions per value to pack, and 16/32-byte
+//     stores of the thread's own pixels -- coalesced across the warp.
+//   * Source rows arrive through a ring of plain bulk copies (cp.async.bulk, one per row, mbarrier
+//     completion); stages are handed back like in the downscaling kernel.
+#ifndef PICHA_B200_RESIZE_UP_CUH
+#define PICHA_B200_RESIZE_UP_CUH
+
+#include "resize_down.cuh"
+
+namespace picha_b200 {
+namespace up {
+
+using fast::lds;
+using fast::smem;
+using fast::smem_u32;
+using fast::VTable;
+
+constexpr int NT = 64;        // threads per CTA
+constexpr int NPX = 4;        // output pixels per thread
+constexpr int NV = 16;        // = NPX * 4 channels
+constexpr int TILE = NT * NPX;   // output pixels per tile
+constexpr int NS = 3;         // ring stages
+constexpr int RS = 8;         // source rows per stage
+constexpr int kHExp = 120;    // horizontal weights are scaled by 2^kHExp
+constexpr int kMaxDepth = 6;
+
+struct UpArgs {
+	int win_bytes;     // bytes of a source row staged per tile (multiple of 16)
+	float hscale;      // 2^kHExp
+};
+
+__host__ __device__ inline int smem_bytes(int win_bytes) { return NS * RS * win_bytes + 2 * NS * 8; }
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct RingState {
+	int stage, slot, nstages;
+	uint32_t parity;
+};
+
+// One stage: the rows [row0, row0 + RS) that exist and belong to the band, copy_bytes of each.
+__device__ __forceinline__ void issue_stage(uint32_t dst, uint32_t bar, const uint8_t *src, long long stride, int row0,
+                                            int row_end, int win_bytes, int copy_bytes) {
+	int rows = row_end - row0;
+	if (rows > RS) rows = RS;
+	fast::mbar_expect_tx_a(bar, rows * copy_bytes);
+	// no loop here: this runs under a per-thread condition, and a loop there makes the compiler treat the
+	// caller's loop state as divergent (the vertical weights would leave the uniform registers)
+#pragma unroll
+	for (int i = 0; i < RS; ++i)
+		if (i < rows) bulk_load(dst + i * win_bytes, src + (row0 + i) * stride, copy_bytes, bar);
+}
+
+template <int DEPTH, bool DEEP, int WPX>
+__global__ void __launch_bounds__(NT, 6)
+resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant__ VTable vt, UpArgs ua) {
+	constexpr int BPP = 4 * Depth<DEEP>::bytes;
+	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
+	constexpr int WPP = DEEP ? 2 : 1;            // 32-bit words per source pixel
+	const int tid = threadIdx.x;
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+	const int x0 = blockIdx.x * TILE;
+	const int sx0 = t.xfirst[x0] / t.align_px * t.align_px;   // tile origin in the source row: 16-byte aligned
+	const int band = blockIdx.y;
+	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
+	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
+	const uint8_t *const simg = src.base + (long long)blockIdx.z * src.step + (long long)sx0 * BPP;
+	// never read past the row's own bytes (the last row of the last image ends the allocation)
+	const int copy_bytes = min(ua.win_bytes, (src.stride - sx0 * BPP) & ~15);
+
+	uint32_t sbase = smem_u32(smem);
+	asm volatile("" : "+r"(sbase));
+	const uint32_t ring = sbase, bars = sbase + NS * RS * ua.win_bytes;
+	const int stage_bytes = RS * ua.win_bytes;
+
+	RingState rs;
+	rs.stage = -1; rs.slot = NS - 1; rs.parity = 1;
+	rs.nstages = (rhi - rlo) / RS + 1;
+	if (tid == 0) {
+		for (int i = 0; i < NS; ++i) {
+			down::mbar_init_a(bars + 8 * i, 1);
+			down::mbar_init_a(bars + 8 * (NS + i), NT / 32);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+		for (int k = 0; k < NS; ++k)
+			if (k < rs.nstages) issue_stage(ring + k * stage_bytes, bars + 8 * k, simg, src.stride, rlo + k * RS, rhi + 1, ua.win_bytes, copy_bytes);
+	}
+
+	// ---- this thread's four output pixels: window start and dense weight block ---------------------
+	const int px0 = x0 + NPX * tid;
+	const bool any = px0 < dst.width;
+	const int ws = any ? t.xfirst[px0] - sx0 : 0;           // first source pixel of the thread's window (tile-relative)
+	float wh[NPX][WPX];
+#pragma unroll
+	for (int p = 0; p < NPX; ++p) {
+		const int px = px0 + p;
+		const bool live = px < dst.width;
+		const int f = live ? t.xfirst[px] - sx0 : 0, c = live ? t.xcount[px] : 0;
+#pragma unroll
+		for (int j = 0; j < WPX; ++j) {
+			const int k = ws + j - f;
+			wh[p][j] = (k >= 0 && k < c) ? t.xw[(long long)px * t.xstride + k] * ua.hscale : 0.0f;
+		}
+	}
+	// byte offset of window pixel j in a staged row; positions behind the staged bytes carry zero weights
+	uint32_t off[WPX];
+#pragma unroll
+	for (int j = 0; j < WPX; ++j) off[j] = min((ws + j) * BPP, copy_bytes - BPP);
+	__syncthreads();   // barrier initialisation is visible
+
+	float win[DEPTH][NV];
+#pragma unroll
+	for (int k = 0; k < DEPTH; ++k)
+#pragma unroll
+		for (int i = 0; i < NV; ++i) win[k][i] = 0.0f;
+
+	uint32_t rowaddr = 0;   // shared address of the next row to read
+	int fleft = 0;
+	auto advance = [&]() {
+		const int prev = rs.slot;
+		if (rs.stage >= 0 && rs.stage + NS < rs.nstages) {
+			__syncwarp();
+			if ((tid & 31) == 0) {
+				uint32_t pending;
+				asm volatile(
+					"{\n\t.reg .b64 st;\n\t"
+					"mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
+					"mbarrier.pending_count.b64 %0, st;\n\t}"
+					: "=r"(pending) : "r"(bars + 8 * (NS + prev)) : "memory");
+				if (pending == 1)
+					issue_stage(ring + prev * stage_bytes, bars + 8 * prev, simg, src.stride, rlo + (rs.stage + NS) * RS, rhi + 1,
+					            ua.win_bytes, copy_bytes);
+			}
+		}
+		++rs.stage;
+		if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
+		fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
+		fleft = RS;
+		rowaddr = ring + rs.slot * stage_bytes;
+	};
+	auto load_row = [&](uint32_t (&raw)[WPX * WPP]) {
+#pragma unroll
+		for (int j = 0; j < WPX; ++j) {
+			if (DEEP) {
+				const uint2 v = lds<uint2>(rowaddr + off[j]);
+				raw[(WPP * j) % (WPX * WPP)] = v.x; raw[(WPP * j + 1) % (WPX * WPP)] = v.y;
+			} else {
+				raw[j] = (uint32_t)lds<int>(rowaddr + off[j]);
+			}
+		}
+		rowaddr += ua.win_bytes;
+		--fleft;
+	};
+
+	uint8_t *const dcol = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * BPP;
+	const int npx = any ? min(NPX, dst.width - px0) : 0;
+
+	uint32_t raw[WPX * WPP];
+	advance();
+	load_row(raw);
+	// Loop state that indexes the constant bank (widx, yidx) is kept apart from anything per-thread: used
+	// in a per-thread address computation it would be held in a vector register, and the weight loads
+	// would follow it there.
+	int yidx = y0 - vt.out_base + 1;                // next entry of ytab
+	int widx = (y0 - vt.out_base) * WS;
+	int need = vt.ytab[yidx - 1];                   // last source row output y needs
+	uint8_t *drow = dcol + (long long)y0 * dst.stride;
+	auto process_row = [&](int r, float (&wrow)[NV]) {
+		// ---- horizontal pass of source row r -------------------------------------------------------
+		float h[NV];   // accumulated apart from the window: the window's old row may still be read by nobody, but
+		               // the prefetch below wants the raw words free early
+#pragma unroll
+		for (int j = 0; j < WPX; ++j) {
+			float u[4];
+			if (DEEP) {
+				u[0] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] & 0xFFFFu);
+				u[1] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] >> 16);
+				u[2] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] & 0xFFFFu);
+				u[3] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] >> 16);
+			} else {
+#pragma unroll
+				for (int c = 0; c < 4; ++c) u[c] = __uint_as_float(__byte_perm(raw[j % (WPX * WPP)], 0, 0x4440 + c));
+			}
+#pragma unroll
+			for (int p = 0; p < NPX; ++p)
+#pragma unroll
+				for (int c = 0; c < 4; ++c) h[4 * p + c] = j == 0 ? wh[p][0] * u[c] : fmaf(wh[p][j], u[c], h[4 * p + c]);
+		}
+		// the next row's pixels, fetched while this row's outputs are computed
+		if (r < rhi) {
+			if (fleft == 0) advance();
+			load_row(raw);
+		}
+#pragma unroll
+		for (int i = 0; i < NV; ++i) wrow[i] = h[i];
+
+		// ---- vertical pass: every output row whose last source row this was ----------------------------
+		// (The loop deliberately has no "y < y1" test: with a second exit condition the compiler holds the
+		// loop state in vector registers and the weights below stop being uniform operands.  The table ends
+		// with a sentinel; at a band boundary inside a launch an output row that shares its last source row
+		// with this band's last output is produced here as well as by the next band -- same values.)
+		while (need == r) {
+			const float *w = vt.wt + widx;
+			uint32_t pv[NV];
+#pragma unroll
+			for (int i = 0; i < NV; ++i) {
+				float a = w[0] * win[0][i];
+#pragma unroll
+				for (int k = 1; k < DEPTH - 1; ++k) a = fmaf(w[k], win[k][i], a);
+				a = __saturatef(fmaf(w[DEPTH - 1], win[DEPTH - 1][i], a));
+				// floor(a * max + 0.5) in the low mantissa bits (round half up like the reference: ties are common
+				// with box and triangle weights, so round-to-nearest-even in a single FMA will not do)
+				pv[i] = __float_as_uint(__fadd_rd(fmaf(a, Depth<DEEP>::maxv, 0.5f), 8388608.0f));
+			}
+			if (DEEP) {
+				uint32_t q[8];
+#pragma unroll
+				for (int i = 0; i < 8; ++i) q[i] = __byte_perm(pv[2 * i], pv[2 * i + 1], 0x5410);
+				if (npx == NPX) {
+					reinterpret_cast<uint4 *>(drow)[0] = make_uint4(q[0], q[1], q[2], q[3]);
+					reinterpret_cast<uint4 *>(drow)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+				} else {
+#pragma unroll
+					for (int p = 0; p < NPX; ++p)
+						if (p < npx) reinterpret_cast<uint2 *>(drow)[p] = make_uint2(q[2 * p], q[2 * p + 1]);
+				}
+			} else {
+				uint32_t q[4];
+#pragma unroll
+				for (int p = 0; p < 4; ++p) {
+					const uint32_t lo = __byte_perm(pv[4 * p], pv[4 * p + 1], 0x0040), hi = __byte_perm(pv[4 * p + 2], pv[4 * p + 3], 0x0040);
+					q[p] = __byte_perm(lo, hi, 0x5410);
+				}
+				if (npx == NPX) {
+					reinterpret_cast<uint4 *>(drow)[0] = make_uint4(q[0], q[1], q[2], q[3]);
+				} else {
+#pragma unroll
+					for (int p = 0; p < NPX; ++p)
+						if (p < npx) reinterpret_cast<uint32_t *>(drow)[p] = q[p];
+				}
+			}
+			need = vt.ytab[yidx];
+			++yidx;
+			widx += WS;
+			drow += dst.stride;
+		}
+	};
+	// Window slots are static: the row loop is unrolled DEPTH times and starts at a multiple of DEPTH
+	// (source row r lives in slot r % DEPTH, which is also how the host lays out the weights).
+	for (int rb = rlo - rlo % DEPTH; rb <= rhi; rb += DEPTH) {
+#pragma unroll
+		for (int k = 0; k < DEPTH; ++k) {
+			const int r = rb + k;
+			if (r >= rlo && r <= rhi) process_row(r, win[k]);
+		}
+	}
+
+	// Never leave with a copy still in flight: wait for every stage that was issued.
+	for (int k = rs.stage + 1; k < rs.nstages && k < rs.stage + NS; ++k) {
+		if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
+		fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
+	}
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+struct UpLaunch {
+	const DevBatch *src, *dst;
+	const FastTables *t;
+	const VTable *vt;
+	UpArgs ua;
+	int n, bands, wpx, overlap;
+	cudaStream_t stream;
+};
+
+template <int DEPTH, bool DEEP, int WPX> cudaError_t launch_one(const UpLaunch &a) {
+	auto kern = resize_up_kernel<DEPTH, DEEP, WPX>;
+	const int smem_total = smem_bytes(a.ua.win_bytes);
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+	if (e != cudaSuccess) return e;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((a.dst->width + TILE - 1) / TILE, a.bands, a.n);
+	cfg.blockDim = dim3(NT);
+	cfg.dynamicSmemBytes = smem_total;
+	cfg.stream = a.stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = a.overlap ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kern, *a.src, *a.dst, *a.t, *a.vt, a.ua);
+}
+
+template <int DEPTH, bool DEEP> cudaError_t launch_wpx(const UpLaunch &a) {
+	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6>(a);
+	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8>(a);
+	return cudaErrorNotSupported;
+}
+
+template <bool DEEP> cudaError_t launch_depth(const UpLaunch &a) {
+	const int d = a.t->depth;
+	if (d <= 3) return launch_wpx<3, DEEP>(a);
+	if (d <= 4) return launch_wpx<4, DEEP>(a);
+	if (d <= 6) return launch_wpx<6, DEEP>(a);
+	return cudaErrorNotSupported;
+}
+
+}  // namespace up
+
+using up::UpLaunch;
+cudaError_t launch_up_u8(const UpLaunch &a);
+cudaError_t launch_up_u16(const UpLaunch &a);
+
+}  // namespace picha_b200
+#endif

@@ -225,4 +225,21 @@ void build_fast_x(const AxisTable &t, FastAxisX &f) {
 	}
 }
 
+void build_flat_rows(const FastAxisX &x, int channels, FlatRows &f) {
+	f = FlatRows();
+	const int n = (int)x.first.size();
+	f.col.resize(n);
+	std::map<std::pair<int, int>, int> seen;
+	for (int i = 0; i < n; ++i) {
+		const std::pair<int, int> key(x.urow[i], (x.first[i] * channels) & 3);
+		auto it = seen.find(key);
+		if (it == seen.end()) {
+			it = seen.emplace(key, (int)f.src.size()).first;
+			f.src.push_back(key.first);
+			f.off.push_back(key.second);
+		}
+		f.col[i] = it->second;
+	}
+}
+
 }  // namespace picha_b200

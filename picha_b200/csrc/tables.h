@@ -73,6 +73,17 @@ struct FastAxisX {
 };
 void build_fast_x(const AxisTable &x, FastAxisX &out);
 
+// Odd channel counts (grey, rgb) run the horizontal pass on the row as a flat float array read in
+// aligned float4 chunks: a column then needs its weight row expanded to one weight per float
+// (each tap repeated `channels` times) and shifted by the column's misalignment off = (first *
+// channels) mod 4.  The expansion happens on the device; this is the list of distinct (row, off)
+// pairs and each column's entry in it.
+struct FlatRows {
+	std::vector<int> col;       // [dst] index into src/off
+	std::vector<int> src, off;  // [count] weight row (FastAxisX::urow numbering), shift in floats
+};
+void build_flat_rows(const FastAxisX &x, int channels, FlatRows &out);
+
 // Filter tag order: src/resize.cc:151-160.  `width` is ResizeOptions::width (ScaledFilter scale).
 void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTable &out);
 
