@@ -94,7 +94,7 @@ __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, in
 struct DownArgs {
 	float xscale;   // factor on the horizontal weights: 2^(149 - kVExp) / max
 	int nb;         // blocks of 4 horizontal taps every column is padded to
-	int direct;     // 4- and 8-byte pixels with an aligned destination: stored from registers
+	int direct;     // destination aligned to the pixel's store unit: pixels are stored from registers (no output tile)
 	int wrows;      // weight rows in shared memory: FastTables::xunique (shared by all columns) or tile_w (one each)
 	int uniq;       // which of the two
 };
@@ -282,17 +282,16 @@ template <> struct PixelAcc<1> {
 	}
 };
 
-// A thread produces P2U output pixels at a time (same row of the group, columns 16 apart): their
+// A thread produces U output pixels at a time (same row of the group, columns NT / GR apart): their
 // loads and FMA chains interleave, which is what hides the shared-memory and FMA latencies here --
 // there are only two or three warps per scheduler.  Every column runs the same `nb` blocks of taps
 // (weights are zero-padded; what lies behind a short window is finite: see the kernel).
-#ifndef PICHA_DOWN_P2U
-#define PICHA_DOWN_P2U 4
-#endif
+// (One instantiation per kernel: with several widths of U linked into the same kernel the row loop's
+// register allocation suffers -- measured, cfg3 +9 %.)
 template <int C, bool DEEP, int GR>
 __device__ __noinline__ void pass2(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
-	constexpr int U = PICHA_DOWN_P2U;
+	constexpr int U = 4;
 	constexpr int GSH = GR == 8 ? 3 : 2;
 	const int total = a.tw * GR;
 	const int g = a.tid & (GR - 1);                // NT is a multiple of GR: the same row for every item
@@ -327,7 +326,7 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 			if (!live[u]) continue;
 			float f[C];
 			acc[u].result(f, off[u]);
-			if ((BPP == 4 || BPP == 8) && a.direct) {
+			if (a.direct) {
 				uint32_t pv[C];
 #pragma unroll
 				for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
@@ -337,15 +336,24 @@ __device__ __noinline__ void pass2(Pass2Args a) {
 					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(lo, hi, 0x5410);
 				} else if (BPP == 4) {
 					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(pv[0], pv[1 % C], 0x5410);
-				} else {
+				} else if (BPP == 8) {
 					*reinterpret_cast<uint2 *>(gp) = make_uint2(__byte_perm(pv[0], pv[1 % C], 0x5410), __byte_perm(pv[2 % C], pv[3 % C], 0x5410));
+				} else if (BPP == 2 && !DEEP) {
+					*reinterpret_cast<uint16_t *>(gp) = (uint16_t)__byte_perm(pv[0], pv[1 % C], 0x0040);
+				} else {
+					// 1, 3 and 6 byte pixels: channel by channel (the output of a downscale is a small part of the traffic)
+#pragma unroll
+					for (int ch = 0; ch < C; ++ch) {
+						if (DEEP) reinterpret_cast<uint16_t *>(gp)[ch] = (uint16_t)pv[ch];
+						else gp[ch] = (uint8_t)pv[ch];
+					}
 				}
 			} else {
 				fast::store_pixel<C, DEEP>(a.sbase + a.outt + g * a.out_stride + xx[u] * BPP, f);
 			}
 		}
 	}
-	if (!((BPP == 4 || BPP == 8) && a.direct)) copy_out<BPP>(a);
+	if (!a.direct) copy_out<BPP>(a);
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
@@ -372,7 +380,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	const int y0 = vt.y_begin + band * t.band_h, y1 = min(vt.y_end, y0 + t.band_h);
 	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
 
-	const bool direct = (BPP == 4 || BPP == 8) && da.direct;
+	const bool direct = da.direct != 0;
 	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived

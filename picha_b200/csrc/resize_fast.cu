@@ -131,8 +131,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		dl.da.uniq = rows > 0 && rows * 2 <= t.tile_w;
 		dl.da.wrows = dl.da.uniq ? rows : t.tile_w;
 		dl.da.xscale = std::ldexp(1.0f, 149 - down::kVExp) / (deep ? 65535.0f : 255.0f);
-		dl.da.direct = (bpp == 4 || bpp == 8) &&
-		               ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (bpp - 1)) == 0;
+		const int store_unit = (bpp == 4 || bpp == 8) ? bpp : (bpp == 2 && !deep) ? 2 : deep ? 2 : 1;
+		dl.da.direct = ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (store_unit - 1)) == 0;
 	}
 	// 4-channel upscales with a shallow row window take the kernel of resize_up.cuh.
 	bool use_up = fy.variant == FastAxisY::kUp && channels == 4 && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
@@ -166,8 +166,24 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		if (up::smem_bytes(ul.ua.win_bytes) > max_dynamic_smem()) use_up = false;
 	}
 	if (use_down) {
-		const char *g = getenv("PICHA_B200_DOWN_G");
-		dl.group = g ? atoi(g) == 8 ? 8 : 4 : 4;
+		// Rows per pass-2 group.  With 4, the eight lanes that share a shared-memory phase of a float4 read
+		// are four rows of two neighbouring columns; they hit distinct banks only if the columns' windows
+		// start the right distance apart (in float4 units: 4 mod 8 with rows one unit apart -- even channel
+		// counts -- or an odd distance with rows two units apart -- odd channel counts).  When that holds
+		// for few column pairs, groups of 8 rows (one column per phase: never a conflict) are worth their
+		// shared memory.
+		int pairs = 0, clean = 0;
+		if (channels != 2) {
+			const int x1 = std::min(dst.width, t.tile_w);
+			for (int x = 0; x + 1 < x1; x += 2) {
+				const int a0 = (host_xfirst[x] * channels) >> 2, a1 = (host_xfirst[x + 1] * channels) >> 2;
+				const int d = (a1 - a0) & 7;
+				++pairs;
+				clean += (channels & 1) ? (d & 1) : d == 4;
+			}
+		}
+		dl.group = pairs > 0 && clean * 4 < pairs * 3 ? 8 : 4;
+		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 ? 8 : 4;
 	}
 	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
@@ -194,7 +210,10 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	const int dh = dst.height;
 	const int ctas_per_sm = use_down || use_up ? 6 : 4;
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
-	long long want = (148LL * ctas_per_sm * 16 + tiles - 1) / tiles;
+	// (the new kernels have a noticeable per-CTA start-up -- tables and a zeroed intermediate in shared
+	// memory, the first stage's latency -- so they get fewer, taller bands: ~6 waves instead of ~16)
+	const int waves = use_down || use_up ? 6 : 16;
+	long long want = (148LL * ctas_per_sm * waves + tiles - 1) / tiles;
 	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
 	if (want > max_bands) want = max_bands;
 	if (want < 1) want = 1;
