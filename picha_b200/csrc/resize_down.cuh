@@ -288,8 +288,11 @@ template <> struct PixelAcc<1> {
 // (weights are zero-padded; what lies behind a short window is finite: see the kernel).
 // (One instantiation per kernel: with several widths of U linked into the same kernel the row loop's
 // register allocation suffers -- measured, cfg3 +9 %.)
+#ifndef PICHA_DOWN_P2_INLINE
+#define PICHA_DOWN_P2_INLINE __noinline__
+#endif
 template <int C, bool DEEP, int GR>
-__device__ __noinline__ void pass2(Pass2Args a) {
+__device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	constexpr int U = 4;
 	constexpr int GSH = GR == 8 ? 3 : 2;
