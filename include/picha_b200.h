@@ -102,6 +102,11 @@ const char *picha_b200_strerror(int status);
 const char *picha_b200_last_error(void);
 /* Kernels this library has launched so far (process-wide, all devices). */
 uint64_t picha_b200_launch_count(void);
+/* Which kernel served the most recent resize launched from the calling thread (diagnostics and
+ * tests; there is nothing like it in the reference): 0 none yet, 1 bit-exact kernel
+ * (resize_exact.cu), 2 generic throughput kernel (resize_fast.cuh), 3 downscaling kernel with
+ * 4-row groups, 4 with 8-row groups (resize_down.cuh), 5 upscaling kernel (resize_up.cuh). */
+int picha_b200_last_resize_kernel(void);
 
 /* ---- format helpers: pixelBytes / pixelChannels / NativeImage::row_stride,
  *      src/picha.h:174-200,212-215 ----------------------------------------------------- */

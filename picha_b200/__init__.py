@@ -18,3 +18,8 @@ def device_count():
 
 def launch_count():
     return lib.picha_b200_launch_count()
+
+
+def last_resize_kernel():
+    """1 bit-exact, 2 generic throughput, 3 / 4 downscaling (4- / 8-row groups), 5 upscaling kernel."""
+    return lib.picha_b200_last_resize_kernel()

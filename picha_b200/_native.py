@@ -54,6 +54,7 @@ SIGNATURES = {
     "picha_b200_strerror": (ctypes.c_char_p, [ctypes.c_int]),
     "picha_b200_last_error": (ctypes.c_char_p, []),
     "picha_b200_launch_count": (ctypes.c_uint64, []),
+    "picha_b200_last_resize_kernel": (ctypes.c_int, []),
     "picha_b200_pixel_bytes": (ctypes.c_int, [ctypes.c_int]),
     "picha_b200_pixel_channels": (ctypes.c_int, [ctypes.c_int]),
     "picha_b200_row_stride": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),

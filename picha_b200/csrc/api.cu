@@ -416,6 +416,7 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	if (e == cudaErrorNotSupported) {
 		launches = 0;
 		e = launch_resize_exact(s, d, n, plan->t, stream, &launches);
+		g_last_resize_kernel = 1;
 	}
 	g_launches += launches;
 	if (e == cudaErrorInvalidValue) { cudaGetLastError(); return PICHA_B200_ERR_UNSUPPORTED; }
@@ -601,6 +602,8 @@ const char *picha_b200_strerror(int status) {
 const char *picha_b200_last_error(void) { return g_last_error.c_str(); }
 
 uint64_t picha_b200_launch_count(void) { return g_launches.load(); }
+
+int picha_b200_last_resize_kernel(void) { return g_last_resize_kernel; }
 
 int picha_b200_pixel_bytes(int pixel) { return pixel_info(pixel).bytes; }
 int picha_b200_pixel_channels(int pixel) { return pixel_info(pixel).channels; }

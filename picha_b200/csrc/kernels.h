@@ -87,5 +87,8 @@ cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uin
 
 int max_dynamic_smem();
 
+// picha_b200_last_resize_kernel(): set by the launchers, read by the C-ABI layer
+extern thread_local int g_last_resize_kernel;
+
 }  // namespace picha_b200
 #endif

@@ -43,6 +43,8 @@ namespace picha_b200 {
 
 using namespace fast;
 
+thread_local int g_last_resize_kernel = 0;
+
 namespace {
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -309,6 +311,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;
 		*launches += 1;
+		g_last_resize_kernel = use_up ? 5 : use_down ? (dl.group == 8 ? 4 : 3) : 2;
 		yb = ye;
 	}
 	return cudaSuccess;

@@ -273,6 +273,46 @@ def test_resize_fast_kernel_multi_tile(gpu, pixel):
         assert_resize_close(got, want, False, (pixel, sw, sh, dw, dh, filt, fw))
 
 
+def test_resize_kernel_variants(gpu, monkeypatch):
+    """Shapes picked for the code paths of the downscaling (csrc/resize_down.cuh) and upscaling
+    (csrc/resize_up.cuh) kernels: pruned end taps and shared weight rows (integer ratios), 4- and
+    8-row horizontal groups (forced both ways), the flat horizontal pass of 1- and 3-channel pixels,
+    several row bands and launches per image, upscales close to 1:1 (widest per-thread window) and
+    with a 6-row vertical window, and outputs narrower than one tile."""
+    P = gpu
+    rng = np.random.default_rng(4242)
+    down = [("rgba", 1024, 600, 256, 150, "lanczos", 1.0), ("rgb", 1200, 640, 160, 160, "cubic", 0.7),
+            ("grey", 999, 777, 333, 111, "mitchel", 1.0), ("greya", 1280, 720, 427, 241, "catmulrom", 1.0),
+            ("r16g16b16", 900, 500, 300, 250, "triangle", 1.0), ("r16g16b16a16", 800, 1200, 237, 300, "lanczos", 1.0),
+            ("rgba", 2000, 3000, 250, 1500, "box", 1.0), ("r16", 700, 900, 100, 450, "cubic", 1.0)]
+    for group in ("4", "8", None):
+        if group is None:
+            monkeypatch.delenv("PICHA_B200_DOWN_G", raising=False)
+        else:
+            monkeypatch.setenv("PICHA_B200_DOWN_G", group)
+        for (pixel, sw, sh, dw, dh, filt, fw) in down:
+            img = rand_image(rng, sw, sh, pixel)
+            want = oracle_resize(img, dw, dh, filt, fw)
+            got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+            assert_resize_close(got, want, False, ("down", group, pixel, sw, sh, dw, dh, filt, fw))
+            assert P.last_resize_kernel() == {"4": 3, "8": 4}.get(group, P.last_resize_kernel())
+            assert P.last_resize_kernel() in (3, 4)
+    up = [("rgba", 300, 200, 1500, 1700, "mitchel", 1.0), ("r16g16b16a16", 257, 400, 771, 1601, "catmulrom", 1.0),
+          ("rgba", 500, 300, 520, 310, "cubic", 1.0), ("r16g16b16a16", 200, 150, 333, 999, "lanczos", 1.5),
+          ("rgba", 64, 300, 150, 1800, "triangle", 1.0), ("rgba", 640, 480, 1280, 960, "box", 1.0)]
+    for (pixel, sw, sh, dw, dh, filt, fw) in up:
+        img = rand_image(rng, sw, sh, pixel)
+        want = oracle_resize(img, dw, dh, filt, fw)
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        assert_resize_close(got, want, False, ("up", pixel, sw, sh, dw, dh, filt, fw))
+        assert P.last_resize_kernel() == 5
+        monkeypatch.setenv("PICHA_B200_OLD_UP", "1")       # the generic kernel on the same shape
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        monkeypatch.delenv("PICHA_B200_OLD_UP")
+        assert P.last_resize_kernel() == 2
+        assert_resize_close(got, want, False, ("up-generic", pixel, sw, sh, dw, dh, filt, fw))
+
+
 def axis_matrix(filt, fw, src, dst, vertical):
     """The reference's filter along one axis as a dense float64 (dst x src) matrix, from the product's
     own contribution table; the vertical one uses the effective (ring-aliased) rows."""
@@ -375,6 +415,8 @@ def test_resize_benchmark_shapes(gpu, cfg):
     fw = 1.0 if "filter" in opts else 0.70
     want = oracle_resize(img, dw, dh, filt, fw)
     got = P.resizeSync(img, dict(opts, width=dw, height=dh))
+    # the kernels the benchmark numbers are about: downscaling (4- / 8-row groups) and upscaling
+    assert P.last_resize_kernel() == {"cfg3": 3, "cfg4": 5, "cfg5": 4}[cfg]
     assert_resize_close(got, want, False, cfg)
     if cfg != "cfg4":
         assert_resize_close(P.resizeSync(img, dict(opts, width=dw, height=dh, exact=True)), want, True, cfg)
