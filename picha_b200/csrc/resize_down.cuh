@@ -365,7 +365,7 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 #endif
 
 template <int DEPTH, bool DEEP, int C, int GR>
-__global__ void __launch_bounds__(NT, PICHA_DOWN_MINB(DEPTH))
+__global__ void __launch_bounds__(NT, GR == 8 ? 4 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
 resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, DownArgs da) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;

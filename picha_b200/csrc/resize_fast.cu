@@ -137,7 +137,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		dl.da.direct = ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (store_unit - 1)) == 0;
 	}
 	// 4-channel upscales with a shallow row window take the kernel of resize_up.cuh.
-	bool use_up = fy.variant == FastAxisY::kUp && channels == 4 && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
+	// Upscales with a shallow row window take the kernel of resize_up.cuh (its stores are whole words
+	// up to 16 bytes: the destination must be 16-byte aligned, which the library's own layout is).
+	bool use_up = fy.variant == FastAxisY::kUp && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
 	              ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)(n > 1 ? dst.step : 0)) & 15) == 0;
 	UpLaunch ul;
 	const int *host_xfirst = t.h_xfirst, *host_xcount = t.h_xcount;
@@ -306,7 +308,18 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				case 8: e = launch_down<false, 4>(dl); break;
 				default: e = launch_down<true, 4>(dl); break;
 			}
-		} else if (use_up) e = deep ? launch_up_u16(ul) : launch_up_u8(ul);
+		} else if (use_up) {
+			switch (channels * 2 + (deep ? 1 : 0)) {
+				case 2: e = launch_up<false, 1>(ul); break;
+				case 3: e = launch_up<true, 1>(ul); break;
+				case 4: e = launch_up<false, 2>(ul); break;
+				case 5: e = launch_up<true, 2>(ul); break;
+				case 6: e = launch_up<false, 3>(ul); break;
+				case 7: e = launch_up<true, 3>(ul); break;
+				case 8: e = launch_up<false, 4>(ul); break;
+				default: e = launch_up<true, 4>(ul); break;
+			}
+		}
 		else if (fy.variant == 0) e = deep ? launch_fast_down_u16(a) : launch_fast_down_u8(a);
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;

@@ -1,13 +1,14 @@
-// Upscaling variant of the fast resize path for 4-channel pixels (rgba, r16g16b16a16); reference:
-// src/resize.cc:66-134.  Included by the resize_up_*.cu instantiation units.
+// Upscaling variant of the fast resize path; reference: src/resize.cc:66-134.  Included by the
+// resize_up_*.cu instantiation units (one per channel count and depth).
 //
 // An upscale is the mirror image of a downscale: the expensive pass is the one that runs at the
 // OUTPUT resolution, so that is the pass that has to be thread-private.  Here that is the vertical
 // pass, and the order is the reference's own -- horizontal first:
-//   * A thread owns 4 consecutive output pixels (16 channel values) of the tile and keeps a window of
-//     DEPTH horizontally-filtered rows of them in registers (DEPTH x 16 floats).
+//   * A thread owns 4 consecutive output pixels (4 x C channel values) of the tile and keeps a window
+//     of DEPTH horizontally-filtered rows of them in registers (DEPTH x 4C floats).
 //   * Horizontal pass, once per SOURCE row: the thread reads the <= WPX source pixels its four
-//     outputs touch straight from the staged row (bytes as subnormal floats, see resize_down.cuh),
+//     outputs touch straight from the staged row (bytes as subnormal floats, see resize_down.cuh;
+//     4-channel pixels as whole words, the others value by value with zero-extending loads),
 //     and multiplies them with a dense 4 x WPX weight block it holds in registers (the block is the
 //     same for every row; entries outside a column's taps are zero).  No intermediate ever goes
 //     through shared memory and there is no CTA-wide barrier in the kernel.
@@ -32,7 +33,6 @@ using fast::VTable;
 
 constexpr int NT = 64;        // threads per CTA
 constexpr int NPX = 4;        // output pixels per thread
-constexpr int NV = 16;        // = NPX * 4 channels
 constexpr int TILE = NT * NPX;   // output pixels per tile
 constexpr int NS = 3;         // ring stages
 constexpr int RS = 8;         // source rows per stage
@@ -69,12 +69,14 @@ __device__ __forceinline__ void issue_stage(uint32_t dst, uint32_t bar, const ui
 		if (i < rows) bulk_load(dst + i * win_bytes, src + (row0 + i) * stride, copy_bytes, bar);
 }
 
-template <int DEPTH, bool DEEP, int WPX>
+template <int DEPTH, bool DEEP, int WPX, int C>
 __global__ void __launch_bounds__(NT, 6)
 resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant__ VTable vt, UpArgs ua) {
-	constexpr int BPP = 4 * Depth<DEEP>::bytes;
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	constexpr int NV = NPX * C;                  // channel values a thread owns
 	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
-	constexpr int WPP = DEEP ? 2 : 1;            // 32-bit words per source pixel
+	// registers per staged pixel: 4-channel pixels travel as 32-bit words, the others as one zero-extended value each
+	constexpr int WPP = C == 4 ? (DEEP ? 2 : 1) : C;
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -162,11 +164,19 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	auto load_row = [&](uint32_t (&raw)[WPX * WPP]) {
 #pragma unroll
 		for (int j = 0; j < WPX; ++j) {
-			if (DEEP) {
+			if (C == 4 && DEEP) {
 				const uint2 v = lds<uint2>(rowaddr + off[j]);
 				raw[(WPP * j) % (WPX * WPP)] = v.x; raw[(WPP * j + 1) % (WPX * WPP)] = v.y;
-			} else {
+			} else if (C == 4) {
 				raw[j] = (uint32_t)lds<int>(rowaddr + off[j]);
+			} else {
+#pragma unroll
+				for (int c = 0; c < C; ++c) {
+					uint32_t v;
+					if (DEEP) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(rowaddr + off[j] + 2 * c) : "memory");
+					else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(rowaddr + off[j] + c) : "memory");
+					raw[(C * j + c) % (WPX * WPP)] = v;
+				}
 			}
 		}
 		rowaddr += ua.win_bytes;
@@ -192,20 +202,23 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		               // the prefetch below wants the raw words free early
 #pragma unroll
 		for (int j = 0; j < WPX; ++j) {
-			float u[4];
-			if (DEEP) {
+			float u[C];
+			if (C == 4 && DEEP) {
 				u[0] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] & 0xFFFFu);
-				u[1] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] >> 16);
-				u[2] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] & 0xFFFFu);
-				u[3] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] >> 16);
+				u[1 % C] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] >> 16);
+				u[2 % C] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] & 0xFFFFu);
+				u[3 % C] = __uint_as_float(raw[(2 * j + 1) % (WPX * WPP)] >> 16);
+			} else if (C == 4) {
+#pragma unroll
+				for (int c = 0; c < C; ++c) u[c] = __uint_as_float(__byte_perm(raw[j % (WPX * WPP)], 0, 0x4440 + c));
 			} else {
 #pragma unroll
-				for (int c = 0; c < 4; ++c) u[c] = __uint_as_float(__byte_perm(raw[j % (WPX * WPP)], 0, 0x4440 + c));
+				for (int c = 0; c < C; ++c) u[c] = __uint_as_float(raw[(C * j + c) % (WPX * WPP)]);
 			}
 #pragma unroll
 			for (int p = 0; p < NPX; ++p)
 #pragma unroll
-				for (int c = 0; c < 4; ++c) h[4 * p + c] = j == 0 ? wh[p][0] * u[c] : fmaf(wh[p][j], u[c], h[4 * p + c]);
+				for (int c = 0; c < C; ++c) h[C * p + c] = j == 0 ? wh[p][0] * u[c] : fmaf(wh[p][j], u[c], h[C * p + c]);
 		}
 		// the next row's pixels, fetched while this row's outputs are computed
 		if (r < rhi) {
@@ -233,32 +246,37 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 				// with box and triangle weights, so round-to-nearest-even in a single FMA will not do)
 				pv[i] = __float_as_uint(__fadd_rd(fmaf(a, Depth<DEEP>::maxv, 0.5f), 8388608.0f));
 			}
-			if (DEEP) {
-				uint32_t q[8];
+			// the thread's 4 pixels are NV / (DEEP ? 2 : 4) whole 32-bit words of the row
+			constexpr int NW = DEEP ? NV / 2 : NV / 4;
+			uint32_t q[NW];
 #pragma unroll
-				for (int i = 0; i < 8; ++i) q[i] = __byte_perm(pv[2 * i], pv[2 * i + 1], 0x5410);
-				if (npx == NPX) {
-					reinterpret_cast<uint4 *>(drow)[0] = make_uint4(q[0], q[1], q[2], q[3]);
-					reinterpret_cast<uint4 *>(drow)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+			for (int i = 0; i < NW; ++i) {
+				if (DEEP) {
+					q[i] = __byte_perm(pv[2 * i], pv[2 * i + 1], 0x5410);
+				} else {
+					const uint32_t lo = __byte_perm(pv[4 * i], pv[4 * i + 1], 0x0040), hi = __byte_perm(pv[4 * i + 2], pv[4 * i + 3], 0x0040);
+					q[i] = __byte_perm(lo, hi, 0x5410);
+				}
+			}
+			if (npx == NPX) {
+				if (NW % 4 == 0) {
+#pragma unroll
+					for (int i = 0; i < NW / 4; ++i) reinterpret_cast<uint4 *>(drow)[i] = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+				} else if (NW % 2 == 0) {
+#pragma unroll
+					for (int i = 0; i < NW / 2; ++i) reinterpret_cast<uint2 *>(drow)[i] = make_uint2(q[2 * i], q[2 * i + 1]);
 				} else {
 #pragma unroll
-					for (int p = 0; p < NPX; ++p)
-						if (p < npx) reinterpret_cast<uint2 *>(drow)[p] = make_uint2(q[2 * p], q[2 * p + 1]);
+					for (int i = 0; i < NW; ++i) reinterpret_cast<uint32_t *>(drow)[i] = q[i];
 				}
 			} else {
-				uint32_t q[4];
+				// the last thread of a row whose width is not a multiple of 4: value by value
 #pragma unroll
-				for (int p = 0; p < 4; ++p) {
-					const uint32_t lo = __byte_perm(pv[4 * p], pv[4 * p + 1], 0x0040), hi = __byte_perm(pv[4 * p + 2], pv[4 * p + 3], 0x0040);
-					q[p] = __byte_perm(lo, hi, 0x5410);
-				}
-				if (npx == NPX) {
-					reinterpret_cast<uint4 *>(drow)[0] = make_uint4(q[0], q[1], q[2], q[3]);
-				} else {
-#pragma unroll
-					for (int p = 0; p < NPX; ++p)
-						if (p < npx) reinterpret_cast<uint32_t *>(drow)[p] = q[p];
-				}
+				for (int i = 0; i < NV; ++i)
+					if (i < npx * C) {
+						if (DEEP) reinterpret_cast<uint16_t *>(drow)[i] = (uint16_t)pv[i];
+						else drow[i] = (uint8_t)pv[i];
+					}
 			}
 			need = vt.ytab[yidx];
 			++yidx;
@@ -293,8 +311,8 @@ struct UpLaunch {
 	cudaStream_t stream;
 };
 
-template <int DEPTH, bool DEEP, int WPX> cudaError_t launch_one(const UpLaunch &a) {
-	auto kern = resize_up_kernel<DEPTH, DEEP, WPX>;
+template <int DEPTH, bool DEEP, int WPX, int C> cudaError_t launch_one(const UpLaunch &a) {
+	auto kern = resize_up_kernel<DEPTH, DEEP, WPX, C>;
 	const int smem_total = smem_bytes(a.ua.win_bytes);
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
 	if (e != cudaSuccess) return e;
@@ -311,25 +329,25 @@ template <int DEPTH, bool DEEP, int WPX> cudaError_t launch_one(const UpLaunch &
 	return cudaLaunchKernelEx(&cfg, kern, *a.src, *a.dst, *a.t, *a.vt, a.ua);
 }
 
-template <int DEPTH, bool DEEP> cudaError_t launch_wpx(const UpLaunch &a) {
-	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6>(a);
-	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8>(a);
+template <int DEPTH, bool DEEP, int C> cudaError_t launch_wpx(const UpLaunch &a) {
+	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6, C>(a);
+	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8, C>(a);
 	return cudaErrorNotSupported;
 }
 
-template <bool DEEP> cudaError_t launch_depth(const UpLaunch &a) {
+template <bool DEEP, int C> cudaError_t launch_depth(const UpLaunch &a) {
 	const int d = a.t->depth;
-	if (d <= 3) return launch_wpx<3, DEEP>(a);
-	if (d <= 4) return launch_wpx<4, DEEP>(a);
-	if (d <= 6) return launch_wpx<6, DEEP>(a);
+	if (d <= 3) return launch_wpx<3, DEEP, C>(a);
+	if (d <= 4) return launch_wpx<4, DEEP, C>(a);
+	if (d <= 6) return launch_wpx<6, DEEP, C>(a);
 	return cudaErrorNotSupported;
 }
 
 }  // namespace up
 
 using up::UpLaunch;
-cudaError_t launch_up_u8(const UpLaunch &a);
-cudaError_t launch_up_u16(const UpLaunch &a);
+// One definition per instantiation unit (channels 1..4, 8- and 16-bit).
+template <bool DEEP, int C> cudaError_t launch_up(const UpLaunch &a);
 
 }  // namespace picha_b200
 #endif

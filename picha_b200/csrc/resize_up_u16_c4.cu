@@ -3,6 +3,6 @@
 
 namespace picha_b200 {
 
-cudaError_t launch_up_u8(const UpLaunch &a) { return up::launch_depth<false>(a); }
+template <> cudaError_t launch_up<true, 4>(const UpLaunch &a) { return up::launch_depth<true, 4>(a); }
 
 }  // namespace picha_b200

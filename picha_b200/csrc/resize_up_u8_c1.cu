@@ -1,0 +1,8 @@
+// Instantiation unit of the upscaling resize kernels: see resize_up.cuh.
+#include "resize_up.cuh"
+
+namespace picha_b200 {
+
+template <> cudaError_t launch_up<false, 1>(const UpLaunch &a) { return up::launch_depth<false, 1>(a); }
+
+}  // namespace picha_b200

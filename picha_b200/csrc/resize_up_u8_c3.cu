@@ -3,6 +3,6 @@
 
 namespace picha_b200 {
 
-cudaError_t launch_up_u16(const UpLaunch &a) { return up::launch_depth<true>(a); }
+template <> cudaError_t launch_up<false, 3>(const UpLaunch &a) { return up::launch_depth<false, 3>(a); }
 
 }  // namespace picha_b200

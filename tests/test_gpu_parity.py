@@ -299,7 +299,10 @@ def test_resize_kernel_variants(gpu, monkeypatch):
             assert P.last_resize_kernel() in (3, 4)
     up = [("rgba", 300, 200, 1500, 1700, "mitchel", 1.0), ("r16g16b16a16", 257, 400, 771, 1601, "catmulrom", 1.0),
           ("rgba", 500, 300, 520, 310, "cubic", 1.0), ("r16g16b16a16", 200, 150, 333, 999, "lanczos", 1.5),
-          ("rgba", 64, 300, 150, 1800, "triangle", 1.0), ("rgba", 640, 480, 1280, 960, "box", 1.0)]
+          ("rgba", 64, 300, 150, 1800, "triangle", 1.0), ("rgba", 640, 480, 1280, 960, "box", 1.0),
+          ("rgb", 333, 222, 1001, 667, "mitchel", 1.0), ("r16g16b16", 250, 180, 521, 377, "cubic", 1.0),
+          ("grey", 400, 300, 1203, 450, "catmulrom", 1.0), ("r16", 300, 200, 450, 901, "lanczos", 1.0),
+          ("greya", 320, 240, 642, 481, "triangle", 1.0), ("r16g16", 256, 256, 1023, 300, "mitchel", 1.0)]
     for (pixel, sw, sh, dw, dh, filt, fw) in up:
         img = rand_image(rng, sw, sh, pixel)
         want = oracle_resize(img, dw, dh, filt, fw)
