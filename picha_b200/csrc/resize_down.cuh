@@ -56,11 +56,14 @@ __host__ __device__ constexpr int tmps(int channels, int group) {
 #define PICHA_DOWN_NS 2
 #endif
 constexpr int NS = PICHA_DOWN_NS;  // ring stages
-constexpr int STAGE_BYTES = 8192;  // 8 rows of 1024 bytes (u8) or 4 rows of 2048 bytes (u16)
+#ifndef PICHA_DOWN_RS
+#define PICHA_DOWN_RS 8
+#endif
+constexpr int STAGE_BYTES = PICHA_DOWN_RS * 1024;  // 8 rows of 1024 bytes (u8) or 4 rows of 2048 bytes (u16)
 constexpr int kVExp = 120;         // vertical weights are scaled by 2^kVExp
 constexpr int kMaxDepth = 8;
 
-__host__ __device__ constexpr int stage_rows(bool deep) { return deep ? 4 : 8; }
+__host__ __device__ constexpr int stage_rows(bool deep) { return deep ? PICHA_DOWN_RS / 2 : PICHA_DOWN_RS; }
 
 // Odd channel counts: float4 chunks of an expanded weight row, (nb + 1) blocks of `channels` chunks.
 __host__ __device__ constexpr int flat_chunks(int channels, int nb) { return channels * (nb + 1); }
@@ -365,7 +368,10 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 #endif
 
 template <int DEPTH, bool DEEP, int C, int GR>
-__global__ void __launch_bounds__(NT, GR == 8 ? 4 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
+#ifndef PICHA_DOWN_MINB8
+#define PICHA_DOWN_MINB8 4
+#endif
+__global__ void __launch_bounds__(NT, GR == 8 ? PICHA_DOWN_MINB8 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
 resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, DownArgs da) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;

@@ -1,36 +1,25 @@
-// Fast fused separable resize for sm_100a (the throughput path; reference: src/resize.cc:66-134).
+// Launch planning of the throughput resize path (reference: src/resize.cc:66-134): picks one of three
+// kernels per shape, cuts the image into row bands, slices the host-built vertical tables into kernel
+// parameters and launches.
 //
-// Work split: one CTA (128 threads) produces a tile of `tile_w` x `band_h` output pixels of one
-// image.  The source rows the tile needs are streamed through a shared-memory ring by TMA
-// (cp.async.bulk.tensor, one elected thread, mbarrier completion), so global latency is hidden by
-// the copy engine, not by occupancy.
+//   resize_down.cuh   downscales (vertical depth <= 8): vertical pass in registers on thread-private
+//                     columns, horizontal pass from shared memory; TMA-staged source rows.
+//   resize_up.cuh     upscales (row window <= 6, <= 8 source pixels per 4 outputs): horizontal pass from the
+//                     staged row, vertical pass in registers on thread-private output pixels; no
+//                     intermediate in shared memory.
+//   resize_fast.cuh   the generic first-generation kernel, for everything else the fast path takes.
 //
-// Pass 1 (vertical, in registers).  A thread owns 8 consecutive channel values of the source row
-// (2 words of u8 data, 4 of u16) -- columns are independent in the vertical direction, so every
-// source byte is read from shared memory once, unpacked once, and used for all the output rows it
-// contributes to.  The per-thread state is either
-//   kDown  a ring of DEPTH accumulators (one per output row currently open), or
-//   kUp    a window of DEPTH unpacked source rows,
-// rotated by loop unrolling so every register index is static.  The vertical weights and the
-// loop bounds are the same for every thread of the grid, so they travel as a kernel parameter
-// (`VTable`, in the constant bank): the compiler keeps them in uniform registers, the FMAs take
-// the weight as a uniform operand (a third vector-register operand halves the FMA issue rate on
-// this part: tools/microbench/row_body.cu) and all loop control stays on the uniform datapath.
-// Finished rows go to shared memory as floats, G output rows per group.
+// All three read each source byte from HBM once (plus band and tile halos), compute with fused FMAs in
+// an order of their own (within +-1 LSB of the reference, not bit-exact: resize_exact.cu is the
+// bit-exact path) and take the vertical weights as warp-uniform operands from the constant bank
+// (`VTable`, a __grid_constant__ kernel parameter; one launch per group of row bands whose tables fit it).
+// Which pass runs first follows from which pass is expensive: the one at the larger resolution must be
+// the thread-private one -- vertical-first for downscales (a horizontal-first pass would push every
+// source value through shared memory as a float once per tap), horizontal-first for upscales (the
+// vertical pass runs at output resolution).
 //
-// Pass 2 (horizontal, from shared memory).  Each thread takes output pixels of the group; lanes of
-// a quarter-warp walk different rows of the group at the same x, so the float4 reads are
-// bank-conflict free and the x weights are broadcast.  Results are packed to u8/u16 into a
-// shared-memory tile and leave as 16-byte coalesced row segments.
-//
-// Why vertical first: the reference filters horizontally first, which on a GPU forces every
-// source value through shared memory as a float once per tap (about 1 byte of shared-memory
-// traffic per MAC, the SM's limit).  Vertical-first keeps 80 % of the MACs of a 4x downscale on
-// thread-private data.  The price is the summation order: results are within +-1 LSB of the
-// reference rather than bit-exact (resize_exact.cu is the bit-exact path).
-//
-// No tensor cores: FP32 FMA on a byte stream, bounded by HBM on one side and FP32 issue on the
-// other (DESIGN.md has the arithmetic).
+// No tensor cores: FP32 FMA on a byte stream, bounded by HBM on one side and FP32 issue on the other
+// (DESIGN.md sections 5.3 and 6 have the arithmetic and the measurements).
 #include <algorithm>
 
 #include <cmath>
@@ -200,7 +189,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	cuuint64_t dims[3] = {row_words, (cuuint64_t)src.height, (cuuint64_t)n};
 	cuuint64_t strides[2] = {(cuuint64_t)src.stride, (cuuint64_t)(n > 1 ? src.step : (int64_t)src.stride * src.height)};
 	if (strides[1] & 15) strides[1] = (strides[1] + 15) & ~15ull;   // n == 1: never dereferenced
-	cuuint32_t box[3] = {256, (cuuint32_t)stage_rows(deep), 1};
+	cuuint32_t box[3] = {256, (cuuint32_t)(use_down ? down::stage_rows(deep) : stage_rows(deep)), 1};
 	cuuint32_t estr[3] = {1, 1, 1};
 	CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.base, dims, strides, box, estr,
 	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -1,5 +1,12 @@
-// Device side of the fast resize path; see resize_fast.cu for the design notes.  Included by the
-// four instantiation units (resize_fast_{down,up}_{u8,u16}.cu), which compile in parallel.
+// The generic (first-generation) kernel of the fast resize path, and the shared-memory / mbarrier /
+// TMA helpers the newer kernels (resize_down.cuh, resize_up.cuh) reuse.  Work split: one CTA (128
+// threads) produces a tile of `tile_w` x `band_h` output pixels of one image from TMA-staged source rows.
+// Pass 1 (vertical, in registers): a thread owns 8 consecutive channel values of the source row and keeps
+// either a ring of DEPTH accumulators (kDown) or a window of DEPTH unpacked source rows (kUp), rotated
+// by loop unrolling so every register index is static; weights come from the constant bank.  Pass 2
+// (horizontal, from shared memory): lanes of a quarter-warp walk different rows of the group at the same
+// x; results are packed into a shared-memory tile and leave as 16-byte coalesced row segments.
+// Included by the four instantiation units (resize_fast_{down,up}_{u8,u16}.cu), which compile in parallel.
 #ifndef PICHA_B200_RESIZE_FAST_CUH
 #define PICHA_B200_RESIZE_FAST_CUH
 #include <cuda.h>
