@@ -11,6 +11,9 @@
 //     2^120 so the sums are ordinary normal floats (w*v * 2^-29); the horizontal weights carry
 //     2^29 / max, so the second pass lands on the [0, 1] scale the pack expects.  Every product is
 //     formed exactly inside the FMA, so nothing is lost relative to unpacking first.
+//   * The accumulators are packed pairs and the vertical MACs fma.rn.f32x2 with the weight as a broadcast
+//     uniform operand (FFMA2 R, R.F32x2, UR.F32, R.F32x2): the same FMA rate (an FFMA2 takes two issue
+//     cycles) with half the instructions in flight -- measured 10 % faster end to end than scalar FFMAs.
 //   * Accumulator slots are fixed (output row y lives in slot y % DEPTH) and the host lays the
 //     weights of a source row out in slot order: the row body is the same code for every row --
 //     no rotation by unrolling, no per-row branches; only the (rare) emit picks a slot.
@@ -52,6 +55,9 @@ static_assert(ROWV == fast::NT * fast::NV, "tile widths are planned once for bot
 __host__ __device__ constexpr int tmps(int channels, int group) {
 	return ROWV + (group == 4 && (channels & 1) ? PICHA_DOWN_ODD_PAD : 4);
 }
+#ifndef PICHA_DOWN_PACKED
+#define PICHA_DOWN_PACKED 1
+#endif
 #ifndef PICHA_DOWN_NS
 #define PICHA_DOWN_NS 2
 #endif
@@ -471,15 +477,37 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
 	};
 
+#if PICHA_DOWN_PACKED
+	// accumulators as packed pairs: fma.rn.f32x2 takes the weight as a broadcast uniform operand
+	// (FFMA2 R, R.F32x2, UR.F32, R.F32x2) and does two MACs in two issue cycles -- the same FMA rate with
+	// half the instructions in flight
+	u64 acc[DEPTH][NV / 2];
+#pragma unroll
+	for (int j = 0; j < DEPTH; ++j)
+#pragma unroll
+		for (int i = 0; i < NV / 2; ++i) acc[j][i] = 0;
+#else
 	float acc[DEPTH][NV];
 #pragma unroll
 	for (int j = 0; j < DEPTH; ++j)
 #pragma unroll
 		for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
+#endif
 
 	// One source row into every open output row.  The value is used as the subnormal float its bits
 	// already are (see the header); weights come from the constant bank as uniform operands.
 	auto body = [&](const uint32_t (&cur)[WPT], const float (&w)[DEPTH]) {
+#if PICHA_DOWN_PACKED
+#pragma unroll
+		for (int i = 0; i < NV; i += 2) {
+			uint32_t b0, b1;
+			if (DEEP) { b0 = cur[(i >> 1) % WPT] & 0xFFFFu; b1 = cur[(i >> 1) % WPT] >> 16; }
+			else { b0 = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4440 + (i & 3)); b1 = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4441 + (i & 3)); }
+			const u64 uu = pair(__uint_as_float(b0), __uint_as_float(b1));
+#pragma unroll
+			for (int j = 0; j < DEPTH; ++j) ffma2(acc[j][i >> 1], uu, pair(w[j], w[j]));
+		}
+#else
 #pragma unroll
 		for (int i = 0; i < NV; ++i) {
 			uint32_t bits;
@@ -489,6 +517,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 #pragma unroll
 			for (int j = 0; j < DEPTH; ++j) acc[j][i] = fmaf(w[j], u, acc[j][i]);
 		}
+#endif
 	};
 	// The weights of a row are fetched from the constant bank into uniform registers one row ahead,
 	// like the data: issued right in front of their first use, the load's latency stalls every row.
@@ -548,9 +577,14 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		for (int j = 0; j < DEPTH; ++j) {
 			if (j == yslot) {
 				if (y >= y0) {
-#if PICHA_DOWN_EMIT_SCALAR
+#if PICHA_DOWN_PACKED
 #pragma unroll
-					for (int i = 0; i < NV; ++i) sts(my_tmp + gcount * (tmps(C, GR) * 4) + (i >> 2) * 1024 + (i & 3) * 4, acc[j][i]);
+					for (int q = 0; q < 4; ++q) {
+						float4 v;
+						unpair(acc[j][2 * q], v.x, v.y);
+						unpair(acc[j][2 * q + 1], v.z, v.w);
+						sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
+					}
 #else
 #pragma unroll
 					for (int q = 0; q < 4; ++q)
@@ -561,8 +595,13 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 				}
 				// in place (tied operand, x * 0): a plain "= 0.0f" makes new values that ptxas pairs up for CS2R and
 				// then shuffles every accumulator of the kernel between two register assignments per output row
+#if PICHA_DOWN_PACKED
+#pragma unroll
+				for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[j][i]) : "l"(0ull));
+#else
 #pragma unroll
 				for (int i = 0; i < NV; ++i) asm volatile("mul.f32 %0, %0, 0f00000000;" : "+f"(acc[j][i]));
+#endif
 			}
 		}
 		++y;
