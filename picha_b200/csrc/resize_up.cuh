@@ -23,6 +23,13 @@
 
 #include "resize_down.cuh"
 
+// Packed window and fma.rn.f32x2 in both passes (see resize_down.cuh): the instantiation units of the
+// 3-channel formats switch it off -- their horizontal pass has no channel pairs with a common weight, and
+// pairing scalars up afterwards costs more than the vertical pass gains (measured).
+#ifndef PICHA_UP_PACKED
+#define PICHA_UP_PACKED 1
+#endif
+
 namespace picha_b200 {
 namespace up {
 
@@ -131,11 +138,20 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	for (int j = 0; j < WPX; ++j) off[j] = min((ws + j) * BPP, copy_bytes - BPP);
 	__syncthreads();   // barrier initialisation is visible
 
+#if PICHA_UP_PACKED
+	// the window as packed pairs: both passes use fma.rn.f32x2 with a broadcast weight (see resize_down.cuh)
+	down::u64 win[DEPTH][NV / 2];
+#pragma unroll
+	for (int k = 0; k < DEPTH; ++k)
+#pragma unroll
+		for (int i = 0; i < NV / 2; ++i) win[k][i] = 0;
+#else
 	float win[DEPTH][NV];
 #pragma unroll
 	for (int k = 0; k < DEPTH; ++k)
 #pragma unroll
 		for (int i = 0; i < NV; ++i) win[k][i] = 0.0f;
+#endif
 
 	uint32_t rowaddr = 0;   // shared address of the next row to read
 	int fleft = 0;
@@ -196,10 +212,17 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	int widx = (y0 - vt.out_base) * WS;
 	int need = vt.ytab[yidx - 1];                   // last source row output y needs
 	uint8_t *drow = dcol + (long long)y0 * dst.stride;
+#if PICHA_UP_PACKED
+	auto process_row = [&](int r, down::u64 (&wrow)[NV / 2]) {
+#else
 	auto process_row = [&](int r, float (&wrow)[NV]) {
+#endif
 		// ---- horizontal pass of source row r -------------------------------------------------------
 		float h[NV];   // accumulated apart from the window: the window's old row may still be read by nobody, but
 		               // the prefetch below wants the raw words free early
+#if PICHA_UP_PACKED
+		down::u64 h2[NV / 2];
+#endif
 #pragma unroll
 		for (int j = 0; j < WPX; ++j) {
 			float u[C];
@@ -215,18 +238,38 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 #pragma unroll
 				for (int c = 0; c < C; ++c) u[c] = __uint_as_float(raw[(C * j + c) % (WPX * WPP)]);
 			}
+#if PICHA_UP_PACKED
+			if (C % 2 == 0) {
+				// channel pairs of a pixel share the weight: packed MACs straight into the pairs of h
 #pragma unroll
-			for (int p = 0; p < NPX; ++p)
+				for (int p = 0; p < NPX; ++p)
 #pragma unroll
-				for (int c = 0; c < C; ++c) h[C * p + c] = j == 0 ? wh[p][0] * u[c] : fmaf(wh[p][j], u[c], h[C * p + c]);
+					for (int c = 0; c < C; c += 2) {
+						const down::u64 uu = down::pair(u[c], u[(c + 1) % C]), ww = down::pair(wh[p][j], wh[p][j]);
+						if (j == 0) asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(h2[(C * p + c) / 2]) : "l"(uu), "l"(ww));
+						else down::ffma2(h2[(C * p + c) / 2], uu, ww);
+					}
+			} else
+#endif
+			{
+#pragma unroll
+				for (int p = 0; p < NPX; ++p)
+#pragma unroll
+					for (int c = 0; c < C; ++c) h[C * p + c] = j == 0 ? wh[p][0] * u[c] : fmaf(wh[p][j], u[c], h[C * p + c]);
+			}
 		}
 		// the next row's pixels, fetched while this row's outputs are computed
 		if (r < rhi) {
 			if (fleft == 0) advance();
 			load_row(raw);
 		}
+#if PICHA_UP_PACKED
+#pragma unroll
+		for (int i = 0; i < NV / 2; ++i) wrow[i] = C % 2 == 0 ? h2[i] : down::pair(h[2 * i], h[2 * i + 1]);
+#else
 #pragma unroll
 		for (int i = 0; i < NV; ++i) wrow[i] = h[i];
+#endif
 
 		// ---- vertical pass: every output row whose last source row this was ----------------------------
 		// (The loop deliberately has no "y < y1" test: with a second exit condition the compiler holds the
@@ -235,13 +278,35 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		// with this band's last output is produced here as well as by the next band -- same values.)
 		while (need == r) {
 			const float *w = vt.wt + widx;
+#if PICHA_UP_PACKED
+			down::u64 part = 0;
+#endif
 			uint32_t pv[NV];
 #pragma unroll
 			for (int i = 0; i < NV; ++i) {
+#if PICHA_UP_PACKED
+				// all but the last tap as packed MACs on the pair (done once per pair, at its even member); the
+				// last tap stays scalar: it carries the saturation, which the packed FMA does not have
+				float a, last;
+				if ((i & 1) == 0) {
+					asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(part) : "l"(win[0][i >> 1]), "l"(down::pair(w[0], w[0])));
+#pragma unroll
+					for (int k = 1; k < DEPTH - 1; ++k) down::ffma2(part, win[k][i >> 1], down::pair(w[k], w[k]));
+				}
+				{
+					float p0, p1, l0, l1;
+					down::unpair(part, p0, p1);
+					down::unpair(win[DEPTH - 1][i >> 1], l0, l1);
+					a = (i & 1) ? p1 : p0;
+					last = (i & 1) ? l1 : l0;
+				}
+				a = __saturatef(fmaf(w[DEPTH - 1], last, a));
+#else
 				float a = w[0] * win[0][i];
 #pragma unroll
 				for (int k = 1; k < DEPTH - 1; ++k) a = fmaf(w[k], win[k][i], a);
 				a = __saturatef(fmaf(w[DEPTH - 1], win[DEPTH - 1][i], a));
+#endif
 				// floor(a * max + 0.5) in the low mantissa bits (round half up like the reference: ties are common
 				// with box and triangle weights, so round-to-nearest-even in a single FMA will not do)
 				pv[i] = __float_as_uint(__fadd_rd(fmaf(a, Depth<DEEP>::maxv, 0.5f), 8388608.0f));

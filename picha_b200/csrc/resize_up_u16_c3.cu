@@ -1,4 +1,5 @@
 // Instantiation unit of the upscaling resize kernels: see resize_up.cuh.
+#define PICHA_UP_PACKED 0   // see resize_up.cuh
 #include "resize_up.cuh"
 
 namespace picha_b200 {
