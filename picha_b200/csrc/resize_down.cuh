@@ -537,18 +537,20 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	advance();
 	load_row(ra);
 	--fleft;
-	int r = rlo;                                   // the row held in ra
 	int y = vt.band_ys[band];                      // oldest open output row
 	int yslot = y % DEPTH;
 	int widx = (rlo - vt.row_base) * WS;           // weights of the row after the one held in ra
 	load_w(wa, widx);
 	widx += WS;
 	int gcount = 0;
-	int need = vt.ytab[y - vt.out_base];           // last source row of output y (fetched one output ahead)
+	// ytab holds, per output row, how many more source rows complete it once the previous output is complete
+	// (the band's first output counts from the band's first row instead: band_n0); fetched one output ahead
+	int tix = y - vt.out_base + 1;
+	int n_next = vt.band_n0[band];
 	while (y < y1) {
-		int n = need - r + 1;                      // output y is complete after this many more rows
-		r += n;
-		need = vt.ytab[y + 1 - vt.out_base];
+		int n = n_next;                            // output y is complete after this many more rows
+		n_next = vt.ytab[tix];
+		++tix;
 		while (n > 0) {
 			if (fleft == 0) advance();
 			int m = min(n, fleft);

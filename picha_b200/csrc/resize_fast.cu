@@ -254,11 +254,17 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			vt.band_rlo[b] = fy.smin[y0];
 			vt.band_rhi[b] = fy.cum[y1 - 1];
 			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[fy.smin[y0]] : y0;
+			vt.band_n0[b] = fy.variant == 0 ? fy.cum[vt.band_ys[b]] - vt.band_rlo[b] + 1 : 0;
 		}
 		const int *ysrc = fy.variant == 0 || use_up ? fy.cum.data() : fy.lo.data();
 		for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
 		// the new kernels look one output ahead; the upscaling kernel's output loop ends on this sentinel
 		vt.ytab[ye - vt.out_base] = use_up || ye >= dh ? -1 : ysrc[ye];
+		if (use_down) {
+			// the downscaling kernel wants row counts: rows that complete output y once y - 1 is complete
+			for (int y = ye; y > vt.out_base; --y) vt.ytab[y - vt.out_base] = y < dh ? fy.cum[y] - fy.cum[y - 1] : 0;
+			vt.ytab[0] = 0;   // a band's first output takes band_n0 instead
+		}
 		// weight rows are re-strided from the host table's stride to the kernel's WS
 		const int first = fy.variant == 0 ? row_lo : yb, last = fy.variant == 0 ? row_hi : ye - 1;
 		if (use_down) {

@@ -50,6 +50,7 @@ struct alignas(16) VTable {
 	int band_rlo[kMaxBands];    // first source row the band touches
 	int band_rhi[kMaxBands];    // last one
 	int band_ys[kMaxBands];     // kDown: output row that is open when row band_rlo arrives (<= the band's first row)
+	int band_n0[kMaxBands];     // resize_down.cuh: source rows from band_rlo that complete output band_ys
 	int ytab[kYtabMax];         // kDown: cum[out_base + i]; kUp: lo[out_base + i]
 	float wt[kWtMax];           // kDown: weights of source row row_base + i / WS; kUp: of output out_base + i / WS
 };
