@@ -140,6 +140,13 @@ int picha_b200_resize_ex(const picha_b200_image *src, picha_b200_image *dst,
 int picha_b200_color_convert(const picha_b200_image *src, picha_b200_image *dst,
                              float r_factor, float g_factor, float b_factor);
 
+/* cmyk_to_rgb, src/jpegcodec.cc:36-42 (called per decoded row from :96): rgb[c] = cmyk[c] * cmyk[3] / 255,
+ * truncating integer arithmetic -- the pixel loop of the JPEG decoder's CMYK path (the
+ * step in front of the hot path; the decoder itself stays on the host).  `cmyk` carries 4 bytes per
+ * pixel (C, M, Y, K as libjpeg delivers them) in an image whose pixel is PICHA_B200_RGBA; `rgb` is
+ * PICHA_B200_RGB of the same size.  Bit-exact. */
+int picha_b200_cmyk_to_rgb(const picha_b200_image *cmyk, picha_b200_image *rgb);
+
 /* Data-parallel batches of independent images (no cross-image step).  device >= 0 runs the
  * whole batch on that GPU; device = -1 shards contiguous blocks of the batch across every
  * GPU of the box, one host thread + streams + pinned staging per GPU, no collective. */
@@ -163,6 +170,8 @@ int picha_b200_resize_device(int n, const picha_b200_image *src0, int64_t src_st
 int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t src_step,
                                     const picha_b200_image *dst0, int64_t dst_step,
                                     float r_factor, float g_factor, float b_factor, void *stream);
+int picha_b200_cmyk_to_rgb_device(int n, const picha_b200_image *cmyk0, int64_t cmyk_step,
+                                  const picha_b200_image *rgb0, int64_t rgb_step, void *stream);
 /* Synthetic pixels, i.i.d. uniform over the full channel range, from a counter-based hash of
  * (seed, image, byte offset in the payload): the same bytes picha_b200.synthetic.fill_host
  * produces, so host and device can regenerate any image of a benchmark batch. */

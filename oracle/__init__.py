@@ -157,6 +157,21 @@ def color_convert(src, sstride, w, h, spixel, dpixel, weights=None, impl="port",
     return dst, dstride
 
 
+def cmyk_to_rgb(src, sstride, w, h, dstride=None):
+    """cmyk_to_rgb of src/jpegcodec.cc:36-42 on a flat uint8 buffer of 4-byte pixels; returns (rgb_buffer, dstride)."""
+    _check_buf(src, sstride, w, h, 4)
+    if dstride is None:
+        dstride = row_stride(w, 0)
+    dst = np.zeros(dstride * h, dtype=np.uint8)
+    lib = port_lib()
+    lib.po_cmyk_to_rgb.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.po_cmyk_to_rgb.restype = ctypes.c_int
+    rc = lib.po_cmyk_to_rgb(src.ctypes.data, sstride, w, h, dst.ctypes.data, dstride)
+    if rc != 0:
+        raise ValueError(f"po_cmyk_to_rgb failed: {rc}")
+    return dst, dstride
+
+
 def contribs(filt, fwidth, srcsize, dstsize, impl="port"):
     """One axis of makeContribs: (left[], right[], woff[], weights[])."""
     f = _idx(filt, FILTERS)

@@ -286,3 +286,19 @@ int po_color_convert(float r, float g, float b,
 	}
 	return 0;
 }
+
+/* src/jpegcodec.cc:36-42: rgb[c] = int(cmyk[c]) * cmyk[3] / 255 (C integer division: truncation),
+ * applied per decoded row (:96). */
+int po_cmyk_to_rgb(const unsigned char *cmyk, int sstride, int w, int h, unsigned char *rgb, int dstride) {
+	if (w < 0 || h < 0) return -1;
+	for (int y = 0; y < h; ++y) {
+		const unsigned char *s = cmyk + (size_t)y * sstride;
+		unsigned char *d = rgb + (size_t)y * dstride;
+		for (int i = 0; i < w; ++i, s += 4, d += 3) {
+			d[0] = (unsigned char)((int)s[0] * s[3] / 255);
+			d[1] = (unsigned char)((int)s[1] * s[3] / 255);
+			d[2] = (unsigned char)((int)s[2] * s[3] / 255);
+		}
+	}
+	return 0;
+}

@@ -33,6 +33,11 @@ int po_color_convert(float r, float g, float b,
                      const unsigned char *src, int sstride, int w, int h, int spixel,
                      unsigned char *dst, int dstride, int dpixel);
 
+/* cmyk_to_rgb (src/jpegcodec.cc:36-42) over every row of a w x h image: 4 bytes per pixel in,
+ * 3 out.  The JPEG codec itself cannot be compiled here (no libjpeg headers), so this one is
+ * pinned by restatement only; the formula is three integer operations. */
+int po_cmyk_to_rgb(const unsigned char *cmyk, int sstride, int w, int h, unsigned char *rgb, int dstride);
+
 #ifdef __cplusplus
 }
 #endif

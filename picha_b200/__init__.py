@@ -7,7 +7,7 @@ path -- ``Image`` (lib/image.js) and ``resize`` / ``resizeSync`` / ``colorConver
 benchmark uses.  Importing it requires the built library; there is no CPU fallback.
 """
 from ._native import EXACT, FORCE_FAST, FILTERS, PIXELS, PichaError, lib   # noqa: F401
-from .api import (colorConvert, colorConvertBatchSync, colorConvertSync, resize,   # noqa: F401
+from .api import (cmykToRgbSync, colorConvert, colorConvertBatchSync, colorConvertSync, resize,   # noqa: F401
                   resizeBatchSync, resizeSync)
 from .image import Image   # noqa: F401
 

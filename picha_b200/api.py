@@ -170,6 +170,20 @@ def colorConvertSync(img, opts):
     return out
 
 
+def cmykToRgbSync(img):
+    """The JPEG decoder's cmyk_to_rgb (src/jpegcodec.cc:36-42) on a whole image: `img` carries C, M, Y, K in
+    an 'rgba' image; the result is 'rgb'.  Not part of picha's JS surface (the reference runs this loop
+    inside decodeJpeg); exposed for the step in front of the hot path."""
+    if not _is_object(img):
+        raise TypeError("expected: cmykToRgbSync(image)")
+    src, keep, out, dst, _ = _prepare_convert(img, {"pixel": "rgb"})
+    if src.pixel != N.PIXELS.index("rgba"):
+        raise N.PichaError(N.ERR_FORMAT_MISMATCH)
+    N.check(N.lib.picha_b200_cmyk_to_rgb(ctypes.byref(src), ctypes.byref(dst)))
+    _ = keep
+    return out
+
+
 def colorConvert(img, opts, cb):
     if not _is_object(img) or not _is_object(opts) or not callable(cb):
         raise TypeError("expected: colorConvert(image, opts, cb)")

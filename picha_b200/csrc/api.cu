@@ -424,9 +424,9 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	return 0;
 }
 
-int run_convert(const DevBatch &s, const DevBatch &d, int n, float r, float g, float b, cudaStream_t stream) {
+int run_convert(const DevBatch &s, const DevBatch &d, int n, float r, float g, float b, cudaStream_t stream, bool cmyk = false) {
 	int launches = 0;
-	cudaError_t e = launch_color_convert(s, d, n, r, g, b, stream, &launches);
+	cudaError_t e = cmyk ? launch_cmyk_to_rgb(s, d, n, stream, &launches) : launch_color_convert(s, d, n, r, g, b, stream, &launches);
 	g_launches += launches;
 	if (e != cudaSuccess) return fail_cuda(e, "color convert kernel launch");
 	return 0;
@@ -444,6 +444,7 @@ struct Op {
 	bool resize;
 	int tag; float width; unsigned flags;   // resize
 	float r, g, b;                          // convert
+	bool cmyk;                              // convert: the JPEG decoder's cmyk_to_rgb instead of doColorConvert
 };
 
 // One image through one lane: upload, kernel, download (all asynchronous on the lane's stream).
@@ -455,7 +456,7 @@ int submit(Device *dev, Lane *lane, const Op &op, const picha_b200_image &s, con
 	if (rc) return rc;
 	DevBatch sb = dev_batch(lane->din.p, 0, sp, s), db = dev_batch(lane->dout.p, 0, dp, d);
 	rc = op.resize ? run_resize(dev, sb, db, 1, op.tag, op.width, op.flags, lane->stream)
-	               : run_convert(sb, db, 1, op.r, op.g, op.b, lane->stream);
+	               : run_convert(sb, db, 1, op.r, op.g, op.b, lane->stream, op.cmyk);
 	if (rc) return rc;
 	return download(lane, d, dp);
 }
@@ -655,6 +656,14 @@ int picha_b200_color_convert(const picha_b200_image *src, picha_b200_image *dst,
 	return run_batch(op, 1, src, dst, default_ordinal());
 }
 
+int picha_b200_cmyk_to_rgb(const picha_b200_image *cmyk, picha_b200_image *rgb) {
+	Op op{};
+	op.resize = false; op.cmyk = true;
+	if (!cmyk || !rgb) return PICHA_B200_ERR_INVALID_IMAGE;
+	if (cmyk->pixel != PICHA_B200_RGBA || rgb->pixel != PICHA_B200_RGB) return PICHA_B200_ERR_FORMAT_MISMATCH;
+	return run_batch(op, 1, cmyk, rgb, default_ordinal());
+}
+
 int picha_b200_resize_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, int filter_tag,
                             float filter_width, unsigned flags, int device) {
 	Op op{};
@@ -706,6 +715,21 @@ int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t
 	DevBatch s = dev_batch(static_cast<uint8_t *>(src0->data), src_step, src0->stride, *src0);
 	DevBatch d = dev_batch(static_cast<uint8_t *>(dst0->data), dst_step, dst0->stride, *dst0);
 	return run_convert(s, d, n, r, g, b, static_cast<cudaStream_t>(stream));
+}
+
+int picha_b200_cmyk_to_rgb_device(int n, const picha_b200_image *cmyk0, int64_t cmyk_step, const picha_b200_image *rgb0,
+                                  int64_t rgb_step, void *stream) {
+	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	int rc = check_convert(cmyk0, rgb0);
+	if (rc) return rc;
+	if (cmyk0->pixel != PICHA_B200_RGBA || rgb0->pixel != PICHA_B200_RGB) return PICHA_B200_ERR_FORMAT_MISMATCH;
+	Device *dev = nullptr;
+	rc = current_device_checked(&dev);
+	if (rc) return rc;
+	if (n == 0) return 0;
+	DevBatch s = dev_batch(static_cast<uint8_t *>(cmyk0->data), cmyk_step, cmyk0->stride, *cmyk0);
+	DevBatch d = dev_batch(static_cast<uint8_t *>(rgb0->data), rgb_step, rgb0->stride, *rgb0);
+	return run_convert(s, d, n, 0.0f, 0.0f, 0.0f, static_cast<cudaStream_t>(stream), true);
 }
 
 int picha_b200_synthetic_fill_device(int n, const picha_b200_image *img0, int64_t step, uint64_t seed,

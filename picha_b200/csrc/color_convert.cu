@@ -32,9 +32,16 @@ template <bool SDEEP, bool DDEEP> __device__ __forceinline__ unsigned depth_conv
 // One pixel, on integer channel values. SC/DC: channel counts. src/colorconvert.cc:24-134.
 // MAGIC: the luma inputs in[0..2] arrive as 0x4B000000 | v (the float 2^23 + v) straight out of a byte
 // permute, instead of as integers -- one instruction less per channel on the bandwidth path.
-template <int SC, bool SDEEP, int DC, bool DDEEP, bool MAGIC = false>
+// CMYK (4 x u8 -> 3 x u8 only): the JPEG decoder's cmyk_to_rgb, src/jpegcodec.cc:36-42 -- integer
+// c * k / 255 per channel, truncating.
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool MAGIC = false, bool CMYK = false>
 __device__ __forceinline__ void convert_pixel(const unsigned *in, unsigned *out, float rf, float gf, float bf) {
 	constexpr unsigned ONE = DDEEP ? 65535u : 255u;
+	if constexpr (CMYK) {
+#pragma unroll
+		for (int c = 0; c < 3; ++c) out[c] = (in[c] * in[3]) / 255u;
+		return;
+	}
 	if constexpr (SC >= 3 && DC <= 2) {          // 3->1, 3->2, 4->1, 4->2: luma (alpha ignored or passed through)
 		float r = MAGIC ? unpack_magic<SDEEP>(in[0]) : unpack_value<SDEEP>(in[0]);
 		float g = MAGIC ? unpack_magic<SDEEP>(in[1]) : unpack_value<SDEEP>(in[1]);
@@ -120,17 +127,17 @@ template <int N> __device__ __forceinline__ void lane_words_store(unsigned *tile
 	}
 }
 
-template <int SC, bool SDEEP, int DC, bool DDEEP>
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
 __device__ __forceinline__ void convert_one_unaligned(const uint8_t *s, uint8_t *d, float rf, float gf, float bf) {
 	unsigned in[4], out[4];
 #pragma unroll
 	for (int c = 0; c < SC; ++c) in[c] = load_channel<SDEEP>(s + c * Depth<SDEEP>::bytes);
-	convert_pixel<SC, SDEEP, DC, DDEEP>(in, out, rf, gf, bf);
+	convert_pixel<SC, SDEEP, DC, DDEEP, false, CMYK>(in, out, rf, gf, bf);
 #pragma unroll
 	for (int c = 0; c < DC; ++c) store_channel<DDEEP>(d + c * Depth<DDEEP>::bytes, out[c]);
 }
 
-template <int SC, bool SDEEP, int DC, bool DDEEP>
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
 __global__ void __launch_bounds__(kWarps * 32)
 convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, float gf, float bf) {
 	constexpr int SW = SC * Depth<SDEEP>::bytes;   // source words per lane per step (= bytes per pixel)
@@ -178,11 +185,11 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, fl
 #pragma unroll
 			for (int p = 0; p < 4; ++p) {
 				unsigned in[4], out[4];
-				constexpr bool LUMA = SC >= 3 && DC <= 2;
+				constexpr bool LUMA = SC >= 3 && DC <= 2 && !CMYK;
 #pragma unroll
 				for (int c = 0; c < SC; ++c)
 					in[c] = (LUMA && c < 3) ? word_get_magic<SDEEP>(mine, p * SC + c) : word_get<SDEEP>(mine, p * SC + c);
-				convert_pixel<SC, SDEEP, DC, DDEEP, LUMA>(in, out, rf, gf, bf);
+				convert_pixel<SC, SDEEP, DC, DDEEP, LUMA, CMYK>(in, out, rf, gf, bf);
 #pragma unroll
 				for (int c = 0; c < DC; ++c) word_put<DDEEP>(packed, p * DC + c, out[c]);
 			}
@@ -200,12 +207,12 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, fl
 			const uint8_t *srow = simg + (long long)y * src.stride;
 			uint8_t *drow = dimg + (long long)y * dst.stride;
 			for (int p = lane; p < npx; p += 32)
-				convert_one_unaligned<SC, SDEEP, DC, DDEEP>(srow + p * SW, drow + p * DW, rf, gf, bf);
+				convert_one_unaligned<SC, SDEEP, DC, DDEEP, CMYK>(srow + p * SW, drow + p * DW, rf, gf, bf);
 		}
 	}
 }
 
-template <int SC, bool SDEEP, int DC, bool DDEEP>
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
 __global__ void __launch_bounds__(256)
 convert_pixels_kernel(DevBatch src, DevBatch dst, float rf, float gf, float bf) {
 	constexpr int SB = SC * Depth<SDEEP>::bytes, DB = DC * Depth<DDEEP>::bytes;
@@ -214,7 +221,7 @@ convert_pixels_kernel(DevBatch src, DevBatch dst, float rf, float gf, float bf) 
 	for (int y = blockIdx.y; y < src.height; y += gridDim.y) {
 		const uint8_t *s = src.base + (long long)blockIdx.z * src.step + (long long)y * src.stride + (long long)x * SB;
 		uint8_t *d = dst.base + (long long)blockIdx.z * dst.step + (long long)y * dst.stride + (long long)x * DB;
-		convert_one_unaligned<SC, SDEEP, DC, DDEEP>(s, d, rf, gf, bf);
+		convert_one_unaligned<SC, SDEEP, DC, DDEEP, CMYK>(s, d, rf, gf, bf);
 	}
 }
 
@@ -252,7 +259,7 @@ int sm_count() {
 	return n;
 }
 
-template <int SC, bool SDEEP, int DC, bool DDEEP>
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
 cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float rf, float gf, float bf,
                         cudaStream_t stream, int *launches) {
 	if (aligned4(src) && aligned4(dst)) {
@@ -268,7 +275,7 @@ cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float r
 			DevBatch s = src, d = dst;
 			s.base += (long long)z0 * src.step;
 			d.base += (long long)z0 * dst.step;
-			convert_rows_kernel<SC, SDEEP, DC, DDEEP><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
+			convert_rows_kernel<SC, SDEEP, DC, DDEEP, CMYK><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
 			*launches += 1;
 		}
 		return cudaGetLastError();
@@ -279,7 +286,7 @@ cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float r
 		s.base += (long long)z0 * src.step;
 		d.base += (long long)z0 * dst.step;
 		dim3 grid((src.width + 255) / 256, src.height < 65535 ? src.height : 65535, nz);
-		convert_pixels_kernel<SC, SDEEP, DC, DDEEP><<<grid, 256, 0, stream>>>(s, d, rf, gf, bf);
+		convert_pixels_kernel<SC, SDEEP, DC, DDEEP, CMYK><<<grid, 256, 0, stream>>>(s, d, rf, gf, bf);
 		*launches += 1;
 	}
 	return cudaGetLastError();
@@ -336,6 +343,14 @@ cudaError_t launch_color_convert(const DevBatch &src, const DevBatch &dst, int n
 		case 7: return launch_src<4, true>(src, dst, n, rf, gf, bf, stream, launches);
 	}
 	return cudaErrorInvalidValue;
+}
+
+// cmyk_to_rgb of every row (src/jpegcodec.cc:36-42,96): the source is 4 bytes per pixel (C, M, Y, K as the
+// decoder delivers them, carried in an rgba image), the destination rgb.
+cudaError_t launch_cmyk_to_rgb(const DevBatch &src, const DevBatch &dst, int n, cudaStream_t stream, int *launches) {
+	if (n <= 0 || src.width <= 0 || src.height <= 0) return cudaSuccess;
+	if (src.pixel != 1 || dst.pixel != 0) return cudaErrorInvalidValue;
+	return launch_pair<4, false, 3, false, true>(src, dst, n, 0.0f, 0.0f, 0.0f, stream, launches);
 }
 
 }  // namespace picha_b200

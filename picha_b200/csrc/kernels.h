@@ -39,6 +39,10 @@ cudaError_t launch_resize_exact(const DevBatch &src, const DevBatch &dst, int n,
 cudaError_t launch_color_convert(const DevBatch &src, const DevBatch &dst, int n,
                                  float rf, float gf, float bf, cudaStream_t stream, int *launches);
 
+// The JPEG decoder's CMYK -> RGB row loop (src/jpegcodec.cc:36-42): rgb[c] = cmyk[c] * cmyk[3] / 255.
+// src: 4-byte pixels (pixel == rgba as the container), dst: rgb.
+cudaError_t launch_cmyk_to_rgb(const DevBatch &src, const DevBatch &dst, int n, cudaStream_t stream, int *launches);
+
 // Device-resident horizontal tables of the fast resize path (tables.h: FastAxisX); the vertical
 // tables (FastAxisY) stay on the host and travel as kernel parameters, a slice per launch.
 struct FastTables {

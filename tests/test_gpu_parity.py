@@ -207,6 +207,27 @@ def test_color_convert_1080p_cfg2(gpu):
         assert np.array_equal(got.rows(), O.payload(want, ws, w, h, to)), to
 
 
+def test_cmyk_to_rgb_bit_exact(gpu):
+    """The JPEG decoder's CMYK row loop (src/jpegcodec.cc:36-42): every (channel, K) pair, a wide image that
+    takes the coalesced kernel, an odd width with row padding, and an unaligned subView."""
+    P = gpu
+    c, k = np.meshgrid(np.arange(256), np.arange(256))
+    full = np.zeros((256, 256, 4), np.uint8)
+    full[..., 0] = c; full[..., 1] = 255 - c; full[..., 2] = (c * 7 + 3) % 256; full[..., 3] = k
+    img = Image({"width": 256, "height": 256, "pixel": "rgba", "data": full.reshape(-1).copy()})
+    want, ws = O.cmyk_to_rgb(np.ascontiguousarray(img.data), img.stride, 256, 256)
+    got = P.cmykToRgbSync(img)
+    assert got.pixel == "rgb" and np.array_equal(got.rows(), O.payload(want, ws, 256, 256, "rgb"))
+    rng = np.random.default_rng(77)
+    for (w, h, pad, off) in [(1921, 37, 8, 0), (130, 9, 0, 3), (5, 4, 4, 1)]:
+        img = rand_image(rng, w, h, "rgba", pad=pad, offset=off)
+        want, ws = O.cmyk_to_rgb(np.ascontiguousarray(img.data), img.stride, w, h)
+        got = P.cmykToRgbSync(img)
+        assert np.array_equal(got.rows(), O.payload(want, ws, w, h, "rgb")), (w, h, pad, off)
+    with pytest.raises(N.PichaError):
+        P.cmykToRgbSync(rand_image(rng, 8, 8, "rgb"))
+
+
 def test_convert_leaves_padding_untouched_and_handles_subviews(gpu):
     P = gpu
     rng = np.random.default_rng(3)

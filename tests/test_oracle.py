@@ -129,3 +129,15 @@ def test_port_matches_live_reference():
             a, _ = O.color_convert(src, ss, w, h, sp, dp, wts, "port")
             b, _ = O.color_convert(src, ss, w, h, sp, dp, wts, "ref")
             assert np.array_equal(a, b), (sp, dp)
+
+
+def test_cmyk_to_rgb_restatement_every_pair():
+    """src/jpegcodec.cc:36-42 on every (channel, K) pair against the formula written out in numpy
+    (the JPEG codec cannot be compiled here, so this one function is pinned by restatement only)."""
+    c, k = np.meshgrid(np.arange(256, dtype=np.int64), np.arange(256, dtype=np.int64))
+    src = np.zeros((256, 256, 4), np.uint8)
+    src[..., 0] = c; src[..., 1] = 255 - c; src[..., 2] = (c * 7 + 3) % 256; src[..., 3] = k
+    got, ds = O.cmyk_to_rgb(src.reshape(-1), 256 * 4, 256, 256)
+    got = got.reshape(256, ds)[:, :768].reshape(256, 256, 3)
+    want = (src[..., :3].astype(np.int64) * src[..., 3:4].astype(np.int64)) // 255
+    assert np.array_equal(got, want.astype(np.uint8))
