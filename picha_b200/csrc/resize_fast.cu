@@ -225,7 +225,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		band_h = (band_h / 2 + 7) / 8 * 8;
 	}
 	t.band_h = band_h;
-	t.depth = depth;
+	// the upscaling kernel is instantiated for windows of 3, 4 and 6 rows: slots are r % that
+	const int updepth = depth <= 3 ? 3 : depth <= 4 ? 4 : 6;
+	t.depth = use_up ? updepth : depth;
 
 	FastLaunch a;
 	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
@@ -279,7 +281,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			for (int i = first; i <= last; ++i) {
 				float *w = vt.wt + (i - first) * WS;
 				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
-				for (int j = 0; j < fy.depth; ++j) w[(fy.lo[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale_up;
+				for (int j = 0; j < fy.depth; ++j) w[(fy.lo[i] + j) % updepth] = fy.wv[(size_t)i * fy.stride + j] * vscale_up;
 			}
 		} else {
 			for (int i = first; i <= last; ++i)

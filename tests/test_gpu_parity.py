@@ -321,6 +321,7 @@ def test_resize_kernel_variants(gpu, monkeypatch):
     up = [("rgba", 300, 200, 1500, 1700, "mitchel", 1.0), ("r16g16b16a16", 257, 400, 771, 1601, "catmulrom", 1.0),
           ("rgba", 500, 300, 520, 310, "cubic", 1.0), ("r16g16b16a16", 200, 150, 333, 999, "lanczos", 1.5),
           ("rgba", 64, 300, 150, 1800, "triangle", 1.0), ("rgba", 640, 480, 1280, 960, "box", 1.0),
+          ("rgba", 320, 200, 700, 900, "mitchel", 1.25), ("r16g16b16a16", 300, 200, 450, 333, "lanczos", 1.2),   # 5-row windows
           ("rgb", 333, 222, 1001, 667, "mitchel", 1.0), ("r16g16b16", 250, 180, 521, 377, "cubic", 1.0),
           ("grey", 400, 300, 1203, 450, "catmulrom", 1.0), ("r16", 300, 200, 450, 901, "lanczos", 1.0),
           ("greya", 320, 240, 642, 481, "triangle", 1.0), ("r16g16", 256, 256, 1023, 300, "mitchel", 1.0)]
