@@ -257,7 +257,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		// multiple of 4 pixels will do and the source row of the tile can be filled to the brim.
 		const int unit = p->x.scale >= 2.0f ? 4 : align_pixels(pi.bytes);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
-			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, 512);
+			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, align_pixels(pi.bytes), 512);
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));

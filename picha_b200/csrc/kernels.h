@@ -70,9 +70,10 @@ constexpr int kFastThreads = 128;        // threads per CTA = source column grou
 constexpr int kFastValuesPerThread = 8;  // channel values of one source row owned by a thread
 constexpr int kFastMaxDepth = 12;
 
-// Largest tile width (output columns, a multiple of `unit`) whose source span fits one CTA row
-// for every tile; 0 if none does.
-int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap);
+// Tile width (output columns, a multiple of `unit`) whose source span, counted from the tile origin
+// (the first tap's pixel rounded down to a multiple of align_px), fits one CTA row for every tile; 0 if
+// none does.
+int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap);
 
 struct FastAxisY;
 

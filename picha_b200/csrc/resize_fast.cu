@@ -62,7 +62,7 @@ int padded_depth(int d) {   // DEPTH the kernel is instantiated with
 
 }  // namespace
 
-int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap) {
+int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap) {
 	const int limit = NT * NV / channels;   // source pixels one CTA row holds
 	// Among the widths whose source span fits, take the one that keeps both passes busiest: pass 1
 	// works on all NT*NV values of the staged row whether the tile needs them or not, pass 2 on
@@ -83,7 +83,8 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 			int lo = xfirst[x0];
 			for (int x = x0; x <= x1; ++x)
 				if (xfirst[x] < lo) lo = xfirst[x];
-			if (lo != xfirst[x0] || hi - xfirst[x0] / unit * unit > limit) ok = false;
+			// the kernels start a tile's staged row at the 16-byte boundary below its first tap (align_px pixels)
+			if (lo != xfirst[x0] || hi - xfirst[x0] / align_px * align_px > limit) ok = false;
 			span_sum += hi - lo;
 		}
 		if (!ok || tiles == 0) continue;

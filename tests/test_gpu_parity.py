@@ -302,7 +302,9 @@ def test_resize_kernel_variants(gpu, monkeypatch):
     with a 6-row vertical window, and outputs narrower than one tile."""
     P = gpu
     rng = np.random.default_rng(4242)
-    down = [("rgba", 1024, 600, 256, 150, "lanczos", 1.0), ("rgb", 1200, 640, 160, 160, "cubic", 0.7),
+    down = [("rgb", 3072, 200, 1024, 100, "lanczos", 1.0), ("grey", 4000, 160, 1333, 80, "lanczos", 1.0),   # tiles filled to the brim
+            ("r16g16b16", 2400, 150, 800, 75, "catmulrom", 1.0),
+            ("rgba", 1024, 600, 256, 150, "lanczos", 1.0), ("rgb", 1200, 640, 160, 160, "cubic", 0.7),
             ("grey", 999, 777, 333, 111, "mitchel", 1.0), ("greya", 1280, 720, 427, 241, "catmulrom", 1.0),
             ("r16g16b16", 900, 500, 300, 250, "triangle", 1.0), ("r16g16b16a16", 800, 1200, 237, 300, "lanczos", 1.0),
             ("rgba", 2000, 3000, 250, 1500, "box", 1.0), ("r16", 700, 900, 100, 450, "cubic", 1.0)]

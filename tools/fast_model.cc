@@ -13,7 +13,7 @@
 
 using namespace picha_b200;
 
-extern "C" int fast_tile_width_model(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int cap) {
+extern "C" int fast_tile_width_model(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap) {
 	const int limit = 128 * 8 / channels;
 	for (int tw = cap / unit * unit; tw >= unit; tw -= unit) {
 		bool ok = true;
@@ -24,7 +24,7 @@ extern "C" int fast_tile_width_model(const int *xfirst, const int *xcount, int d
 				if (xfirst[x] + xcount[x] > hi) hi = xfirst[x] + xcount[x];
 				if (xfirst[x] < lo) lo = xfirst[x];
 			}
-			if (lo != xfirst[x0] || hi - xfirst[x0] / unit * unit > limit) ok = false;
+			if (lo != xfirst[x0] || hi - xfirst[x0] / align_px * align_px > limit) ok = false;
 		}
 		if (ok) return tw;
 	}
@@ -44,7 +44,7 @@ extern "C" int fast_model(int tag, float width, const uint8_t *src, int sstride,
 	const int bpp = channels * (deep ? 2 : 1);
 	int unit = 16;
 	while (unit > 1 && (unit / 2 * bpp) % 16 == 0) unit /= 2;
-	const int tile_w = fy.variant < 0 ? 0 : fast_tile_width_model(fx.first.data(), fx.count.data(), dw, channels, unit, 256);
+	const int tile_w = fy.variant < 0 ? 0 : fast_tile_width_model(fx.first.data(), fx.count.data(), dw, channels, unit, unit, 256);
 	info[0] = fy.variant; info[1] = fy.depth; info[2] = tile_w; info[3] = 0; info[4] = fx.taps; info[5] = band_h;
 	if (fy.variant < 0 || tile_w == 0) return 1;
 	(void)force_variant;
