@@ -340,6 +340,15 @@ def test_resize_kernel_variants(gpu, monkeypatch):
         assert_resize_close(got, want, False, ("up-generic", pixel, sw, sh, dw, dh, filt, fw))
 
 
+def test_resize_random_shapes(gpu):
+    """tools/fuzz_parity.py with a fixed seed: random formats, filters, filter scales, strides and independent
+    x / y ratios between 1:5 up and 9:1 down, default path, against the oracle."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "120", "11"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def axis_matrix(filt, fw, src, dst, vertical):
     """The reference's filter along one axis as a dense float64 (dst x src) matrix, from the product's
     own contribution table; the vertical one uses the effective (ring-aliased) rows."""

@@ -1,0 +1,45 @@
+"""Randomised parity of the default resize path against the oracle (run on a GPU box):
+python tools/fuzz_parity.py [cases] [seed].  Prints every case out of tolerance with the kernel that
+served it and exits non-zero if there was one."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import oracle as O
+import picha_b200 as P
+from picha_b200 import _native as N
+from picha_b200.image import Image, PIXEL_NAMES
+
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+bad, served = 0, {}
+for i in range(cases):
+    pixel = PIXEL_NAMES[rng.integers(0, 8)]
+    filt = N.FILTERS[rng.integers(0, 6)]
+    fw = float(rng.choice([0.7, 1.0, 1.0, 1.3, 2.0]))
+    sw, sh = int(rng.integers(130, 2600)), int(rng.integers(130, 700))
+    rx, ry = float(np.exp(rng.uniform(np.log(0.2), np.log(9.0)))), float(np.exp(rng.uniform(np.log(0.2), np.log(9.0))))
+    dw, dh = max(1, int(sw / rx)), max(1, int(sh / ry))
+    if dw * dh > 6_000_000 or dw > 8000 or dh > 4000:
+        continue
+    bpp = O.PIXEL_BYTES[O.PIXELS.index(pixel)]
+    stride = ((sw * bpp + 3) & ~3) + int(rng.choice([0, 0, 4, 12]))
+    img = Image({"width": sw, "height": sh, "pixel": pixel, "stride": stride,
+                 "data": rng.integers(0, 256, stride * sh, dtype=np.uint8)})
+    try:
+        want, ws = O.resize(np.ascontiguousarray(img.data), stride, sw, sh, pixel, dw, dh, filt, fw)
+    except Exception:
+        continue                      # shapes the reference itself rejects (total weight 0)
+    got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+    k = P.last_resize_kernel()
+    served[k] = served.get(k, 0) + 1
+    a = np.ascontiguousarray(got.rows())
+    b = np.ascontiguousarray(O.payload(want, ws, dw, dh, pixel))
+    if bpp // O.PIXEL_CHANNELS[O.PIXELS.index(pixel)] == 2:
+        a, b = a.view(np.uint16), b.view(np.uint16)
+    d = np.abs(a.astype(np.int64) - b.astype(np.int64))
+    ok = d.max() <= 1 and (d.mean() <= 0.05 if d.size >= 4096 else (d > 0).sum() <= max(1, int(0.05 * d.size)))
+    if not ok:
+        bad += 1
+        print("OUT OF TOLERANCE", pixel, sw, sh, "->", dw, dh, filt, fw, "stride", stride, "kernel", k, "max", int(d.max()), "mean", float(d.mean()))
+print("cases by kernel (1 exact, 2 generic, 3/4 down, 5 up):", dict(sorted(served.items())), "bad:", bad)
+sys.exit(1 if bad else 0)
