@@ -1,5 +1,5 @@
 """Randomised parity of the default resize path against the oracle (run on a GPU box):
-python tools/fuzz_parity.py [cases] [seed].  Prints every case out of tolerance with the kernel that
+python tests/fuzz_parity.py [cases] [seed].  Prints every case out of tolerance with the kernel that
 served it and exits non-zero if there was one."""
 import os, sys
 import numpy as np

@@ -341,11 +341,11 @@ def test_resize_kernel_variants(gpu, monkeypatch):
 
 
 def test_resize_random_shapes(gpu):
-    """tools/fuzz_parity.py with a fixed seed: random formats, filters, filter scales, strides and independent
+    """tests/fuzz_parity.py with a fixed seed: random formats, filters, filter scales, strides and independent
     x / y ratios between 1:5 up and 9:1 down, default path, against the oracle."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "120", "11"], capture_output=True, text=True)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fuzz_parity.py"), "120", "11"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
