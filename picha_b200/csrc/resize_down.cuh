@@ -71,14 +71,15 @@ constexpr int kMaxDepth = 8;
 
 __host__ __device__ constexpr int stage_rows(bool deep) { return deep ? PICHA_DOWN_RS / 2 : PICHA_DOWN_RS; }
 
-// Odd channel counts: float4 chunks of an expanded weight row, (nb + 1) blocks of `channels` chunks.
-__host__ __device__ constexpr int flat_chunks(int channels, int nb) { return channels * (nb + 1); }
+// Odd channel counts: float4 chunks of an expanded weight row, nb blocks of `channels` chunks (a block is
+// 4 * channels floats there; the host sizes nb so that the longest window plus 3 floats of misalignment fits).
+__host__ __device__ constexpr int flat_chunks(int channels, int nb) { return channels * nb; }
 
 struct SmemLayout {
 	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, bars, total;
 };
 
-// nb: blocks of 4 horizontal taps; wrows: weight rows held in shared memory (the plan's distinct
+// nb: blocks of the horizontal pass (DownArgs::nb); wrows: weight rows held in shared memory (the plan's distinct
 // rows, or one per column of the tile); direct: pixels go straight to global memory (no output tile).
 __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct) {
 	SmemLayout L;
@@ -102,7 +103,7 @@ __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, in
 
 struct DownArgs {
 	float xscale;   // factor on the horizontal weights: 2^(149 - kVExp) / max
-	int nb;         // blocks of 4 horizontal taps every column is padded to
+	int nb;         // blocks every column's horizontal pass runs: 4 taps each (even channel counts), 4 * C floats (odd)
 	int direct;     // destination aligned to the pixel's store unit: pixels are stored from registers (no output tile)
 	int wrows;      // weight rows in shared memory: FastTables::xunique (shared by all columns) or tile_w (one each)
 	int uniq;       // which of the two
@@ -324,7 +325,7 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 			off[u] = e.y & 3;
 		}
 		constexpr int WSTEP = (C & 1) ? 16 * C : 32, VSTEP = 16 * C;   // bytes per block: 4 taps (even C), 4 * C floats (odd C)
-		const int blocks = (C & 1) ? a.nb + 1 : a.nb;
+		const int blocks = a.nb;
 		for (int kb = 0; kb < blocks; ++kb) {
 #pragma unroll
 			for (int u = 0; u < U; ++u) {

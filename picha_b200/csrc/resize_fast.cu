@@ -117,7 +117,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		float wmax = 0;
 		for (float w : fy.wv) wmax = std::fmax(wmax, std::fabs(w));
 		if (!(wmax < 128.0f)) use_down = false;      // weights carry 2^120 in that kernel
-		dl.da.nb = (t.xtaps + 3) / 4;
+		dl.da.nb = (channels & 1) ? (channels * t.xtaps + 3 + 4 * channels - 1) / (4 * channels) : (t.xtaps + 3) / 4;
 		// few distinct weight rows (integer and small p/q ratios): the tile keeps just those
 		const int rows = (channels & 1) ? t.xe_count[channels == 3] : t.xunique;
 		dl.da.uniq = rows > 0 && rows * 2 <= t.tile_w;
