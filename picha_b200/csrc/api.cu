@@ -250,13 +250,29 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		build_flat_rows(fx, ci ? 3 : 1, flat[ci]);
 		o_ecol[ci] = put_i(flat[ci].col); o_esrc[ci] = put_i(flat[ci].src); o_eoff[ci] = put_i(flat[ci].off);
 	}
+	// Conditioning: sum |w| of an output's taps is how much the filter amplifies rounding differences.
+	// It is <= 2 per axis for every filter at sane widths, but lanczos and catmulrom narrowed to
+	// filterScale ~0.5 have upscaling phases whose weights nearly cancel before makeContribs normalises
+	// them (src/resize.cc:41-47): sums of hundreds, thousands, or not finite at all.  Only the reference's
+	// own summation order reproduces its result there, so those plans stay with the bit-exact kernel.
+	auto amplification = [](const AxisTable &t) {
+		float worst = 0.0f;
+		for (int i = 0; i < t.dst_size; ++i) {
+			float sum = 0.0f;
+			for (int k = 0; k < t.count[i]; ++k) sum += std::fabs(t.w[t.start[i] + k]);
+			if (!(sum <= 1e30f)) return INFINITY;   // infinite or NaN weights
+			if (sum > worst) worst = sum;
+		}
+		return worst;
+	};
+	const bool well_conditioned = amplification(p->x) * amplification(p->y) <= 8.0f;
 	for (int px = 0; px < kNumPixels; ++px) {
 		const PixelInfo pi = pixel_info(px);
 		// Tile widths: multiples of the 16-byte pixel group when the destination is the big side (vector
 		// stores on every tile); when the image shrinks by 2x or more the destination is small, so any
 		// multiple of 4 pixels will do and the source row of the tile can be filled to the brim.
 		const int unit = p->x.scale >= 2.0f ? 4 : align_pixels(pi.bytes);
-		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone ? 0
+		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone || !well_conditioned ? 0
 			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, align_pixels(pi.bytes), 512);
 	}
 

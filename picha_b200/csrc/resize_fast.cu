@@ -112,7 +112,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	if (!encode) return cudaErrorNotSupported;
 	// Downscales whose accumulator ring is at most 8 deep take the kernel of resize_down.cuh.
 	bool use_down = fy.variant == FastAxisY::kDown && depth <= down::kMaxDepth;
-	DownLaunch dl;
+	DownLaunch dl{};
 	if (use_down) {
 		float wmax = 0;
 		for (float w : fy.wv) wmax = std::fmax(wmax, std::fabs(w));
@@ -131,7 +131,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// up to 16 bytes: the destination must be 16-byte aligned, which the library's own layout is).
 	bool use_up = fy.variant == FastAxisY::kUp && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
 	              ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)(n > 1 ? dst.step : 0)) & 15) == 0;
-	UpLaunch ul;
+	UpLaunch ul{};
 	const int *host_xfirst = t.h_xfirst, *host_xcount = t.h_xcount;
 	const float *host_xw = t.h_xw;
 	if (use_up) {
@@ -230,9 +230,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	const int updepth = depth <= 3 ? 3 : depth <= 4 ? 4 : 6;
 	t.depth = use_up ? updepth : depth;
 
-	FastLaunch a;
+	FastLaunch a{};
 	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
-	VTable vt;
+	VTable vt{};   // (zeroed: the kernels never read past what is filled below, but the block travels to the device whole)
 	a.vt = &vt;
 	dl.map = &map; dl.dst = &dst; dl.t = &t; dl.vt = &vt; dl.n = n; dl.channels = channels; dl.smem_bytes = smem_total;
 	dl.stream = stream;

@@ -349,6 +349,27 @@ def test_resize_random_shapes(gpu):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_resize_ill_conditioned_filters_take_the_exact_kernel(gpu):
+    """lanczos / catmulrom narrowed to filterScale 0.5 have upscaling phases whose taps nearly cancel, and
+    makeContribs (src/resize.cc:41-47) normalises them into weights of +-hundreds, +-thousands or non-finite
+    values.  Nothing but the reference's own summation order reproduces those outputs, so such plans must be
+    served by the bit-exact kernel even at sizes the throughput kernels would otherwise take (found by
+    tests/fuzz_parity.py in wild mode)."""
+    import picha_b200 as P
+    rng = np.random.default_rng(77)
+    for pixel, sw, sh, dw, dh, filt, fw in [("r16g16b16a16", 588, 1301, 187, 2849, "catmulrom", 0.5),
+                                            ("greya", 804, 777, 46, 2919, "catmulrom", 0.5),
+                                            ("r16g16b16", 1500, 1305, 6888, 177, "lanczos", 0.5)]:
+        img = rand_image(rng, sw, sh, pixel)
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        assert P.last_resize_kernel() == 1, (pixel, filt, fw)
+        assert_resize_close(got, oracle_resize(img, dw, dh, filt, fw), True, (pixel, sw, sh, dw, dh, filt, fw))
+    # the same filters at their usual widths are well conditioned and keep the throughput kernels
+    img = rand_image(rng, 588, 1301, "r16g16b16a16")
+    P.resizeSync(img, {"width": 187, "height": 2849, "filter": "catmulrom"})
+    assert P.last_resize_kernel() != 1
+
+
 def axis_matrix(filt, fw, src, dst, vertical):
     """The reference's filter along one axis as a dense float64 (dst x src) matrix, from the product's
     own contribution table; the vertical one uses the effective (ring-aliased) rows."""
