@@ -379,7 +379,7 @@ template <int DEPTH, bool DEEP, int C, int GR>
 #define PICHA_DOWN_MINB8 4
 #endif
 __global__ void __launch_bounds__(NT, GR == 8 ? PICHA_DOWN_MINB8 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
-resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
+resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, DownArgs da) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	constexpr int RSK = stage_rows(DEEP);
@@ -414,12 +414,13 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(smap) : "memory");   // the descriptor slot is reused (see map_slot)
 		constexpr int BOXES = DEEP ? 2 : 1;
 		for (int k = 0; k < NS && k < rs.nstages; ++k) {
 			fast::mbar_expect_tx_a(bars + 8 * k, STAGE_BYTES);
 #pragma unroll
 			for (int b = 0; b < BOXES; ++b)
-				fast::tma_load_3d_a(ring + k * STAGE_BYTES + b * RSK * 1024, &smap, bars + 8 * k, word0 + b * 256, rlo + k * RSK, blockIdx.z);
+				fast::tma_load_3d_a(ring + k * STAGE_BYTES + b * RSK * 1024, smap, bars + 8 * k, word0 + b * 256, rlo + k * RSK, blockIdx.z);
 		}
 	}
 	// this tile's horizontal tables -> shared memory: weights scaled and duplicated (packed-FMA operands)
@@ -473,7 +474,7 @@ resize_down_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		faddr += 1024;
 	};
 	auto advance = [&]() {
-		rs = ring_advance<DEEP>(&smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
+		rs = ring_advance<DEEP>(smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
 		fleft = RSK;
 		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
 	};
@@ -659,7 +660,7 @@ template <int DEPTH, bool DEEP, int C, int GR> cudaError_t launch_group(const Do
 	attr[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = a.overlap ? 1 : 0;
-	return cudaLaunchKernelEx(&cfg, kern, *a.map, *a.dst, *a.t, *a.vt, a.da);
+	return cudaLaunchKernelEx(&cfg, kern, a.map, *a.dst, *a.t, *a.vt, a.da);
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {

@@ -24,6 +24,9 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "resize_up.cuh"
 #include "tables.h"
@@ -95,6 +98,25 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 		if (score > best_score * 1.02) { best_score = score; best = tw; }   // prefer wider tiles on near-ties
 	}
 	return best;
+}
+
+// Device-resident TMA descriptors: one 128-byte slot per resize call from a ring per device.  A slot comes
+// round again after kMapSlots calls, long after the kernels of its previous use have finished; the kernels
+// acquire-fence the tensormap proxy before their first copy so a cached copy of the old contents is not used.
+static CUtensorMap *map_slot() {
+	constexpr unsigned kMapSlots = 4096;
+	static std::mutex mu;
+	static std::map<int, std::pair<CUtensorMap *, unsigned>> rings;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+	std::lock_guard<std::mutex> lock(mu);
+	auto it = rings.find(dev);
+	if (it == rings.end()) {
+		CUtensorMap *p = nullptr;
+		if (cudaMalloc((void **)&p, kMapSlots * sizeof(CUtensorMap)) != cudaSuccess) return nullptr;
+		it = rings.emplace(dev, std::make_pair(p, 0u)).first;
+	}
+	return it->second.first + (it->second.second++ % kMapSlots);
 }
 
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &tables,
@@ -196,6 +218,14 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 	                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
+	// The kernels fetch the descriptor from global memory, not from their parameter block: a slot
+	// of a per-device ring, written in stream order ahead of the launches.
+	CUtensorMap *dmap = map_slot();
+	if (!dmap) return cudaErrorMemoryAllocation;
+	{
+		cudaError_t ce = cudaMemcpyAsync(dmap, &map, sizeof(map), cudaMemcpyHostToDevice, stream);   // pageable source: staged before the call returns
+		if (ce != cudaSuccess) return ce;
+	}
 
 	// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, tall strips (little
 	// vertical halo) when it is large; multiples of 8 rows; small enough that one band's vertical
@@ -231,10 +261,10 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	t.depth = use_up ? updepth : depth;
 
 	FastLaunch a{};
-	a.map = &map; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
+	a.map = dmap; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
 	VTable vt{};   // (zeroed: the kernels never read past what is filled below, but the block travels to the device whole)
 	a.vt = &vt;
-	dl.map = &map; dl.dst = &dst; dl.t = &t; dl.vt = &vt; dl.n = n; dl.channels = channels; dl.smem_bytes = smem_total;
+	dl.map = dmap; dl.dst = &dst; dl.t = &t; dl.vt = &vt; dl.n = n; dl.channels = channels; dl.smem_bytes = smem_total;
 	dl.stream = stream;
 	const float vscale = std::ldexp(1.0f, down::kVExp);
 	ul.src = &src; ul.dst = &dst; ul.t = &t; ul.vt = &vt; ul.n = n; ul.stream = stream;

@@ -442,7 +442,7 @@ template <bool DEEP, int XS> __device__ __forceinline__ void run_pass2(const Pas
 #endif
 template <int VARIANT, int DEPTH, bool DEEP, int XS>
 __global__ void __launch_bounds__(NT, (VARIANT == 0 && DEPTH <= 4 ? PICHA_FAST_MIN_CTAS + 1 : DEPTH <= 6 ? PICHA_FAST_MIN_CTAS : 1))
-resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastTables t,
+resize_fast_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, int channels) {
 	constexpr int WPT = DEEP ? 4 : 2;            // 32-bit words of a source row per thread
 	constexpr int RSK = stage_rows(DEEP);        // rows per ring stage
@@ -471,13 +471,14 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 		mbar_expect_tx(bar, RSK * L.row_bytes);
 		uint8_t *d = smem + L.ring + (k % NS) * RSK * L.row_bytes;
 #pragma unroll
-		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RSK * 1024, &smap, bar, word0 + b * 256, rlo + k * RSK, blockIdx.z);
+		for (int b = 0; b < BOXES; ++b) tma_load_3d(d + b * RSK * 1024, smap, bar, word0 + b * 256, rlo + k * RSK, blockIdx.z);
 	};
 
 	if (tid == 0) {
 		for (int i = 0; i < NS; ++i) mbar_init(bars + i, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(smap) : "memory");   // the descriptor slot is reused (see map_slot)
 		for (int k = 0; k < NS - 1 && k < nstages; ++k) issue_stage(k);
 	}
 	// this tile's horizontal tables -> shared memory
@@ -499,7 +500,7 @@ resize_fast_kernel(const __grid_constant__ CUtensorMap smap, DevBatch dst, FastT
 	auto next_stage = [&]() {
 		++stage;
 		if (++slot == NS) { slot = 0; parity ^= 1; }
-		ring_advance<DEEP>(&smap, sbase + L.ring, sbase + L.bars, stage + NS - 1 < nstages ? stage + NS - 1 : -1, word0, rlo,
+		ring_advance<DEEP>(smap, sbase + L.ring, sbase + L.bars, stage + NS - 1 < nstages ? stage + NS - 1 : -1, word0, rlo,
 		                   blockIdx.z, sbase + L.bars + 8 * slot, parity, tid);
 		rows_left = RSK;
 		doff = sbase + L.ring + slot * RSK * L.row_bytes + thread_byte;
@@ -681,7 +682,7 @@ template <int VARIANT, int DEPTH, bool DEEP, int XS> cudaError_t launch_one(cons
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
 	if (e != cudaSuccess) return e;
 	dim3 grid((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
-	kern<<<grid, NT, a.smem_bytes, a.stream>>>(*a.map, *a.dst, *a.t, *a.vt, a.channels);
+	kern<<<grid, NT, a.smem_bytes, a.stream>>>(a.map, *a.dst, *a.t, *a.vt, a.channels);
 	return cudaGetLastError();
 }
 
