@@ -592,6 +592,7 @@ void picha_b200_shutdown(void) {
 			delete l;
 		}
 		d->plans.clear();
+		release_resize_descriptors(d->id);
 		delete d;
 	}
 	g_devices.assign(g_devices.size(), nullptr);

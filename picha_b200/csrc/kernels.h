@@ -86,6 +86,8 @@ struct FastAxisY;
 // parameter block.
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &t,
                                const FastAxisY &fy, cudaStream_t stream, int *launches);
+// Frees the TMA descriptor ring launch_resize_fast keeps on `device` (current and idle); the next call makes a new one.
+void release_resize_descriptors(int device);
 
 cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uint64_t first_image,
                                   cudaStream_t stream, int *launches);

@@ -103,20 +103,30 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 // Device-resident TMA descriptors: one 128-byte slot per resize call from a ring per device.  A slot comes
 // round again after kMapSlots calls, long after the kernels of its previous use have finished; the kernels
 // acquire-fence the tensormap proxy before their first copy so a cached copy of the old contents is not used.
+static std::mutex g_map_mu;
+static std::map<int, std::pair<CUtensorMap *, unsigned>> g_map_rings;   // device -> (ring, next slot)
+
 static CUtensorMap *map_slot() {
 	constexpr unsigned kMapSlots = 4096;
-	static std::mutex mu;
-	static std::map<int, std::pair<CUtensorMap *, unsigned>> rings;
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-	std::lock_guard<std::mutex> lock(mu);
-	auto it = rings.find(dev);
-	if (it == rings.end()) {
+	std::lock_guard<std::mutex> lock(g_map_mu);
+	auto it = g_map_rings.find(dev);
+	if (it == g_map_rings.end()) {
 		CUtensorMap *p = nullptr;
 		if (cudaMalloc((void **)&p, kMapSlots * sizeof(CUtensorMap)) != cudaSuccess) return nullptr;
-		it = rings.emplace(dev, std::make_pair(p, 0u)).first;
+		it = g_map_rings.emplace(dev, std::make_pair(p, 0u)).first;
 	}
 	return it->second.first + (it->second.second++ % kMapSlots);
+}
+
+// picha_b200_shutdown: the calling thread has selected `device` and synchronised it.
+void release_resize_descriptors(int device) {
+	std::lock_guard<std::mutex> lock(g_map_mu);
+	auto it = g_map_rings.find(device);
+	if (it == g_map_rings.end()) return;
+	cudaFree(it->second.first);
+	g_map_rings.erase(it);
 }
 
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &tables,
