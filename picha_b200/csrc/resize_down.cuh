@@ -407,6 +407,8 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	rs.stage = -1; rs.slot = NS - 1; rs.parity = 1;
 	rs.nstages = (rhi + 1 - rlo) / RSK + 1;        // rows rlo .. rhi + 1: every row is prefetched one ahead
 
+	// the descriptor slot is reused (see map_slot in resize_fast.cu); lane 0 of any warp may issue a refill
+	if ((tid & 31) == 0) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(smap) : "memory");
 	if (tid == 0) {
 		for (int i = 0; i < NS; ++i) {
 			mbar_init_a(bars + 8 * i, 1);
@@ -414,7 +416,6 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(smap) : "memory");   // the descriptor slot is reused (see map_slot)
 		constexpr int BOXES = DEEP ? 2 : 1;
 		for (int k = 0; k < NS && k < rs.nstages; ++k) {
 			fast::mbar_expect_tx_a(bars + 8 * k, STAGE_BYTES);
