@@ -459,10 +459,28 @@ def cfg1_latency(args):
 
 # ---- the reference arm: the reference's own CPU implementation on the host cores ----------------------
 
+def _fill_host_fn():
+    """picha_b200/synthetic.py loaded by path: the reference arm must not import the picha_b200 package
+    (that would map libpicha_b200.so into the reference's process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_picha_synthetic", os.path.join(ROOT, "picha_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.fill_host
+
+
+def shared_config(key, world):
+    """The `config` object both arms print (the driver compares them)."""
+    w = RESIZE_WORKLOADS.get(key) or CONVERT_WORKLOADS[key]
+    return {"workload": w["name"], "images_per_gpu": w["batch"],
+            "parallelism": f"dp{world} (sharded by image, no collective)",
+            "l2": "GPU arm: inputs larger than L2 (per-step input >= 2 GB vs 126 MB L2), no explicit flush"}
+
+
 def run_reference_arm(args):
     import numpy as np
     import oracle as O
-    from picha_b200.synthetic import fill_host
+    fill_host = _fill_host_fn()
 
     key = args.workload
     kind = "reference" if O.have_ref() else "port"
@@ -506,8 +524,9 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "output_mpix_per_s", "value": round(value, 2), "unit": "Mpix/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "filter": w.get("filter") or ("cubic" if key in RESIZE_WORKLOADS else None),
-                       "host_threads": threads},
+            "config": shared_config(key, max(1, args.gpus)),
+            "notes": {"filter": w.get("filter") or ("cubic" if key in RESIZE_WORKLOADS else None), "host_threads": threads,
+                      "timing": "wall clock around each step on the host", "step": sample},
             "cpu_baseline": {"value": round(value, 2), "unit": "Mpix/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 2), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -527,7 +546,7 @@ def main():
                                                    "('auto' = the other BASELINE configs at N=1, 'none')")
     ap.add_argument("--e2e-batch", type=int, default=32, help="images per end-to-end step per GPU")
     ap.add_argument("--cpu-threads", type=int, default=64)
-    ap.add_argument("--ref-per-thread", type=int, default=1)
+    ap.add_argument("--ref-per-thread", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -586,10 +605,8 @@ def main():
             "metric": "output_mpix_per_s", "value": round(res["value"], 1), "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(res["ms_per_step"], 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "images_per_gpu": res["images_per_gpu"],
-                       "parallelism": f"dp{world} (sharded by image, no collective)",
-                       "l2": "inputs larger than L2 (per-step input >= 2 GB vs 126 MB L2); no explicit flush",
-                       "timing": "CUDA events on the launching stream, max over ranks"},
+            "config": shared_config(key, world),
+            "notes": {"timing": "CUDA events on the launching stream, max over ranks"},
             "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "roofline": res["roofline"], "cpu_baseline": res.get("cpu_baseline"),
         }

@@ -90,6 +90,13 @@ def have_ref() -> bool:
     return ref_lib() is not None
 
 
+def _impl(impl):
+    """"auto" = the compiled reference (oracle/_ref) when it is present, else the C port."""
+    if impl == "auto":
+        return "ref" if have_ref() else "port"
+    return impl
+
+
 def _idx(name_or_idx, table):
     return table.index(name_or_idx) if isinstance(name_or_idx, str) else int(name_or_idx)
 
@@ -104,9 +111,10 @@ def _check_buf(buf, stride, width, height, bpp):
     assert buf.size >= stride * (height - 1) + width * bpp
 
 
-def resize(src, sstride, sw, sh, pixel, dw, dh, filt="cubic", fwidth=0.70, impl="port", dstride=None,
+def resize(src, sstride, sw, sh, pixel, dw, dh, filt="cubic", fwidth=0.70, impl="auto", dstride=None,
            dst=None):
     """resizeImage on a flat uint8 buffer; returns (dst_buffer, dstride)."""
+    impl = _impl(impl)
     p = _idx(pixel, PIXELS)
     f = _idx(filt, FILTERS)
     bpp = PIXEL_BYTES[p]
@@ -133,8 +141,9 @@ def resolve_color_settings(r=float("nan"), g=float("nan"), b=float("nan")):
     return float(out[0]), float(out[1]), float(out[2])
 
 
-def color_convert(src, sstride, w, h, spixel, dpixel, weights=None, impl="port", dstride=None, dst=None):
+def color_convert(src, sstride, w, h, spixel, dpixel, weights=None, impl="auto", dstride=None, dst=None):
     """doColorConvert on a flat uint8 buffer; returns (dst_buffer, dstride)."""
+    impl = _impl(impl)
     sp = _idx(spixel, PIXELS)
     dp = _idx(dpixel, PIXELS)
     _check_buf(src, sstride, w, h, PIXEL_BYTES[sp])
@@ -172,8 +181,9 @@ def cmyk_to_rgb(src, sstride, w, h, dstride=None):
     return dst, dstride
 
 
-def contribs(filt, fwidth, srcsize, dstsize, impl="port"):
+def contribs(filt, fwidth, srcsize, dstsize, impl="auto"):
     """One axis of makeContribs: (left[], right[], woff[], weights[])."""
+    impl = _impl(impl)
     f = _idx(filt, FILTERS)
     left = np.zeros(dstsize, np.int32)
     right = np.zeros(dstsize, np.int32)

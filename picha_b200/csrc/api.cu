@@ -10,6 +10,7 @@
 #include "../../include/picha_b200.h"
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a tool injects itself (nsys, ncu --nvtx)
 
 #include <atomic>
 #include <cmath>
@@ -30,6 +31,12 @@
 namespace picha_b200 {
 
 namespace {
+
+// NVTX range around a C-ABI call (tracing row)
+struct Range {
+	explicit Range(const char *name) { nvtxRangePushA(name); }
+	~Range() { nvtxRangePop(); }
+};
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
@@ -547,6 +554,13 @@ int current_device_checked(Device **out) {
 
 }  // namespace
 
+int sm_count() {
+	int dev = 0, v = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+	if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+	return v;
+}
+
 int max_dynamic_smem() {
 	int dev = 0, v = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return 48 * 1024;
@@ -656,6 +670,7 @@ void picha_b200_resolve_color_settings(double red, double green, double blue, fl
 
 int picha_b200_resize_ex(const picha_b200_image *src, picha_b200_image *dst, int filter_tag, float filter_width,
                          unsigned flags) {
+	Range nvtx_range("picha_b200_resize_ex");
 	Op op{};
 	op.resize = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags;
 	if (!src || !dst) return PICHA_B200_ERR_INVALID_IMAGE;
@@ -667,6 +682,7 @@ int picha_b200_resize(const picha_b200_image *src, picha_b200_image *dst, int fi
 }
 
 int picha_b200_color_convert(const picha_b200_image *src, picha_b200_image *dst, float r, float g, float b) {
+	Range nvtx_range("picha_b200_color_convert");
 	Op op{};
 	op.resize = false; op.r = r; op.g = g; op.b = b;
 	if (!src || !dst) return PICHA_B200_ERR_INVALID_IMAGE;
@@ -674,6 +690,7 @@ int picha_b200_color_convert(const picha_b200_image *src, picha_b200_image *dst,
 }
 
 int picha_b200_cmyk_to_rgb(const picha_b200_image *cmyk, picha_b200_image *rgb) {
+	Range nvtx_range("picha_b200_cmyk_to_rgb");
 	Op op{};
 	op.resize = false; op.cmyk = true;
 	if (!cmyk || !rgb) return PICHA_B200_ERR_INVALID_IMAGE;
@@ -683,6 +700,7 @@ int picha_b200_cmyk_to_rgb(const picha_b200_image *cmyk, picha_b200_image *rgb) 
 
 int picha_b200_resize_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, int filter_tag,
                             float filter_width, unsigned flags, int device) {
+	Range nvtx_range("picha_b200_resize_batch");
 	Op op{};
 	op.resize = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags;
 	return run_batch(op, n, srcs, dsts, device);
@@ -690,6 +708,7 @@ int picha_b200_resize_batch(int n, const picha_b200_image *srcs, picha_b200_imag
 
 int picha_b200_color_convert_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, float r, float g,
                                    float b, int device) {
+	Range nvtx_range("picha_b200_color_convert_batch");
 	Op op{};
 	op.resize = false; op.r = r; op.g = g; op.b = b;
 	return run_batch(op, n, srcs, dsts, device);
@@ -708,6 +727,7 @@ void picha_b200_host_free(void *p) {
 
 int picha_b200_resize_device(int n, const picha_b200_image *src0, int64_t src_step, const picha_b200_image *dst0,
                              int64_t dst_step, int filter_tag, float filter_width, unsigned flags, void *stream) {
+	Range nvtx_range("picha_b200_resize_device");
 	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
 	int rc = check_resize(src0, dst0, filter_tag, filter_width);
 	if (rc) return rc;
@@ -722,6 +742,7 @@ int picha_b200_resize_device(int n, const picha_b200_image *src0, int64_t src_st
 
 int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t src_step, const picha_b200_image *dst0,
                                     int64_t dst_step, float r, float g, float b, void *stream) {
+	Range nvtx_range("picha_b200_color_convert_device");
 	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
 	int rc = check_convert(src0, dst0);
 	if (rc) return rc;
@@ -736,6 +757,7 @@ int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t
 
 int picha_b200_cmyk_to_rgb_device(int n, const picha_b200_image *cmyk0, int64_t cmyk_step, const picha_b200_image *rgb0,
                                   int64_t rgb_step, void *stream) {
+	Range nvtx_range("picha_b200_cmyk_to_rgb_device");
 	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
 	int rc = check_convert(cmyk0, rgb0);
 	if (rc) return rc;
@@ -751,6 +773,7 @@ int picha_b200_cmyk_to_rgb_device(int n, const picha_b200_image *cmyk0, int64_t 
 
 int picha_b200_synthetic_fill_device(int n, const picha_b200_image *img0, int64_t step, uint64_t seed,
                                      uint64_t first_image, void *stream) {
+	Range nvtx_range("picha_b200_synthetic_fill_device");
 	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
 	int rc = check_image(img0);
 	if (rc) return rc;

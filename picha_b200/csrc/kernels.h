@@ -93,6 +93,7 @@ cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uin
                                   cudaStream_t stream, int *launches);
 
 int max_dynamic_smem();
+int sm_count();   // SMs of the current device (B200: 148)
 
 // picha_b200_last_resize_kernel(): set by the launchers, read by the C-ABI layer
 extern thread_local int g_last_resize_kernel;

@@ -247,7 +247,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// (the new kernels have a noticeable per-CTA start-up -- tables and a zeroed intermediate in shared
 	// memory, the first stage's latency -- so they get fewer, taller bands: ~6 waves instead of ~16)
 	const int waves = use_down || use_up ? 6 : 16;
-	long long want = (148LL * ctas_per_sm * waves + tiles - 1) / tiles;
+	long long want = ((long long)sm_count() * ctas_per_sm * waves + tiles - 1) / tiles;
 	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
 	if (want > max_bands) want = max_bands;
 	if (want < 1) want = 1;

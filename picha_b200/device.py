@@ -55,8 +55,9 @@ class DeviceBatch:
         view[:, :rows.shape[1]] = rows.to(self.device)
 
 
-def resize(src, dst, filter="cubic", filter_scale=None, exact=False, fast=False):
-    """dst[i] = resizeImage(src[i]) for every image of the batch, on the current stream."""
+def resize(src, dst, filter=None, filter_scale=None, exact=False, fast=False):
+    """dst[i] = resizeImage(src[i]) for every image of the batch, on the current stream.  Options resolve like
+    getResizeOptions (src/resize.cc:173-198): no filter key = cubic at width 0.70, a named filter = width 1.0."""
     tag_out, width_out = ctypes.c_int(0), ctypes.c_float(0)
     has_filter = filter is not None
     N.check(N.lib.picha_b200_resolve_resize_options(int(has_filter), N.FILTERS.index(filter) if has_filter else 0,

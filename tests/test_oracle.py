@@ -13,6 +13,14 @@ import pytest
 import oracle as O
 
 
+@pytest.fixture(params=["port", "ref"])
+def impl(request):
+    """Both checkers are pinned: the C restatement always, the compiled reference where it was built."""
+    if request.param == "ref" and not O.have_ref():
+        pytest.skip("oracle/_ref not built (no reference checkout here)")
+    return request.param
+
+
 def _image_from_rows(rows, pixel):
     h = rows.shape[0]
     w = rows.shape[1]
@@ -23,28 +31,28 @@ def _image_from_rows(rows, pixel):
     return buf, stride, w, h
 
 
-def test_resize_fixture(fixtures):
+def test_resize_fixture(fixtures, impl):
     """test/resize.js:17-30: resize(test2.jpg, 32x24, default opts) vs test2.png (bound < 2; exact here)."""
     buf, stride, w, h = _image_from_rows(fixtures["test2_jpg_rgb"], "rgb")
-    dst, ds = O.resize(buf, stride, w, h, "rgb", 32, 24, "cubic", 0.70)
+    dst, ds = O.resize(buf, stride, w, h, "rgb", 32, 24, "cubic", 0.70, impl)
     got = O.payload(dst, ds, 32, 24, "rgb")
     gold = fixtures["test2_png_rgb"].reshape(24, -1)
     assert np.abs(got.astype(int) - gold.astype(int)).mean() < 2
     assert np.array_equal(got, gold)
 
 
-def test_grey_fixture(fixtures):
+def test_grey_fixture(fixtures, impl):
     """test/color_convert.js:22-29: rgba -> greya equals greytest.png exactly."""
     buf, stride, w, h = _image_from_rows(fixtures["test_png_rgba"], "rgba")
-    dst, ds = O.color_convert(buf, stride, w, h, "rgba", "greya")
+    dst, ds = O.color_convert(buf, stride, w, h, "rgba", "greya", None, impl)
     assert np.array_equal(O.payload(dst, ds, w, h, "greya"), fixtures["greytest_png_greya"].reshape(h, -1))
 
 
-def test_grey_colour_grey_invariant(fixtures):
+def test_grey_colour_grey_invariant(fixtures, impl):
     """test/color_convert.js:30-39."""
     buf, stride, w, h = _image_from_rows(fixtures["greytest_png_greya"], "greya")
-    rgba, rs = O.color_convert(buf, stride, w, h, "greya", "rgba")
-    back, bs = O.color_convert(rgba, rs, w, h, "rgba", "greya")
+    rgba, rs = O.color_convert(buf, stride, w, h, "greya", "rgba", None, impl)
+    back, bs = O.color_convert(rgba, rs, w, h, "rgba", "greya", None, impl)
     assert np.array_equal(O.payload(back, bs, w, h, "greya"), O.payload(buf, stride, w, h, "greya"))
 
 
@@ -58,13 +66,13 @@ def test_port_matches_committed_reference_vectors(ref_vectors):
         if kind == 0:
             p, f, sw, sh, dw, dh = (int(v) for v in row[2:8])
             fw, ss = float(row[8]), int(row[9])
-            dst, ds = O.resize(ref_vectors[f"rs{k}_src"], ss, sw, sh, p, dw, dh, f, np.float32(fw))
+            dst, ds = O.resize(ref_vectors[f"rs{k}_src"], ss, sw, sh, p, dw, dh, f, np.float32(fw), "port")
             assert np.array_equal(O.payload(dst, ds, dw, dh, p), ref_vectors[f"rs{k}_dst"]), ("resize", p, f, sw, sh, dw, dh, fw)
             n_rs += 1
         else:
             sp, dp, w, h, wi = (int(v) for v in row[2:7])
             ss = int(row[9])
-            dst, ds = O.color_convert(ref_vectors[f"cc{k}_src"], ss, w, h, sp, dp, weights[wi])
+            dst, ds = O.color_convert(ref_vectors[f"cc{k}_src"], ss, w, h, sp, dp, weights[wi], "port")
             assert np.array_equal(O.payload(dst, ds, w, h, dp), ref_vectors[f"cc{k}_dst"]), ("convert", sp, dp, wi)
             n_cc += 1
     assert n_rs >= 150 and n_cc >= 64
@@ -84,9 +92,9 @@ def test_depth_identities(ref_vectors):
     t = ref_vectors["tab_u16_ident_fill"].reshape(-1, 2)
     assert np.array_equal(t[:, 0], v16) and (t[:, 1] == 65535).all()
     # and the same through the port, plus the u8 identity
-    d, _ = O.color_convert(v8.astype(np.uint8), 256, 256, 1, "grey", "greya")
+    d, _ = O.color_convert(v8.astype(np.uint8), 256, 256, 1, "grey", "greya", None, "port")
     assert np.array_equal(d[:512].reshape(-1, 2)[:, 0], v8) and (d[:512].reshape(-1, 2)[:, 1] == 255).all()
-    d, _ = O.color_convert(v16.astype(np.uint16).view(np.uint8), 131072, 65536, 1, "r16", "grey")
+    d, _ = O.color_convert(v16.astype(np.uint16).view(np.uint8), 131072, 65536, 1, "r16", "grey", None, "port")
     assert np.array_equal(d[:65536], ref_vectors["tab_u16_to_u8"])
 
 
@@ -94,7 +102,7 @@ def test_contribs_match_reference_tables(ref_vectors):
     for name, (f, fw, s, dn) in {"cfg3x": (1, 1.0, 3840, 960), "cfg3y": (1, 1.0, 2160, 540),
                                  "cfg5x": (0, 0.7, 1920, 256), "cfg5y": (0, 0.7, 1080, 256),
                                  "cfg4": (3, 1.0, 2048, 4096), "cfg1": (0, 0.7, 50, 100)}.items():
-        l, r, o, w = O.contribs(f, np.float32(fw), s, dn)
+        l, r, o, w = O.contribs(f, np.float32(fw), s, dn, "port")
         assert np.array_equal(l, ref_vectors[f"tab_{name}_left"])
         assert np.array_equal(r, ref_vectors[f"tab_{name}_right"])
         assert np.array_equal(w.view(np.uint32), ref_vectors[f"tab_{name}_w"].view(np.uint32))
