@@ -62,11 +62,21 @@ __host__ __device__ constexpr int tmps(int channels, int group) {
 #define PICHA_DOWN_NS 2
 #endif
 constexpr int NS = PICHA_DOWN_NS;  // ring stages
+#ifndef PICHA_DOWN_PF
+#define PICHA_DOWN_PF 0
+#endif
+constexpr int PF = PICHA_DOWN_PF;  // stages prefetched into L2 beyond the ring (0: none)
 #ifndef PICHA_DOWN_RS
 #define PICHA_DOWN_RS 8
 #endif
 constexpr int STAGE_BYTES = PICHA_DOWN_RS * 1024;  // 8 rows of 1024 bytes (u8) or 4 rows of 2048 bytes (u16)
 constexpr int kVExp = 120;         // vertical weights are scaled by 2^kVExp
+// Table row of a source row: its DEPTH vertical weights in slot order, then one word of event flags (an even
+// number of words: the row is fetched with 8-byte uniform loads).
+__host__ __device__ constexpr int weight_stride(int depth) { return (depth + 2) & ~1; }
+constexpr uint32_t kEvCount = 7;   // outputs completed by this row
+constexpr uint32_t kEvStage = 8;   // the row after this one is the last of its ring stage: hand the stage back, wait for the next
+constexpr uint32_t kEvMask = kEvCount | kEvStage;
 constexpr int kMaxDepth = 8;
 
 __host__ __device__ constexpr int stage_rows(bool deep) { return deep ? PICHA_DOWN_RS / 2 : PICHA_DOWN_RS; }
@@ -149,11 +159,18 @@ struct RingState {
 };
 
 template <bool DEEP>
-__device__ __forceinline__ RingState ring_advance(const CUtensorMap *map, uint32_t ring, uint32_t bars, RingState rs, int word0,
+__device__ __noinline__ RingState ring_advance(const CUtensorMap *map, uint32_t ring, uint32_t bars, RingState rs, int word0,
                                                   int row0, int img, int tid) {
 	constexpr int RSK = stage_rows(DEEP);
 	constexpr int BOXES = DEEP ? 2 : 1;          // TMA boxes are at most 256 elements wide
 	const int prev = rs.slot;
+#ifdef PICHA_DOWN_NO_REFILL      // (timing experiments only: the ring is filled once and re-read; no copies, no waits)
+	if (rs.stage >= NS - 1) {
+		++rs.stage;
+		if (++rs.slot == NS) rs.slot = 0;
+		return rs;
+	}
+#endif
 	if (rs.stage >= 0 && rs.stage + NS < rs.nstages) {
 		__syncwarp();
 		if ((tid & 31) == 0) {
@@ -171,6 +188,11 @@ __device__ __forceinline__ RingState ring_advance(const CUtensorMap *map, uint32
 				for (int b = 0; b < BOXES; ++b)
 					fast::tma_load_3d_a(ring + prev * STAGE_BYTES + b * RSK * 1024, map, bars + 8 * prev, word0 + b * 256,
 					                    row0 + (rs.stage + NS) * RSK, img);
+				if (PF > 0 && rs.stage + NS + PF < rs.nstages) {
+#pragma unroll
+					for (int b = 0; b < BOXES; ++b)
+						fast::tma_prefetch_3d_a(map, word0 + b * 256, row0 + (rs.stage + NS + PF) * RSK, img);
+				}
 			}
 		}
 	}
@@ -383,7 +405,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
                    const __grid_constant__ VTable vt, DownArgs da) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	constexpr int RSK = stage_rows(DEEP);
-	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
+	constexpr int WS = weight_stride(DEPTH);     // floats per table row: DEPTH weights and the row's event flags
 	constexpr int WPT = DEEP ? 8 : 4;            // 32-bit words of a source row per thread
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_one
@@ -405,7 +427,9 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 
 	RingState rs;
 	rs.stage = -1; rs.slot = NS - 1; rs.parity = 1;
-	rs.nstages = (rhi + 1 - rlo) / RSK + 1;        // rows rlo .. rhi + 1: every row is prefetched one ahead
+	// rows rlo .. rhi + 2: every row is prefetched one ahead, and the row before a stage's last one already waits
+	// for the next stage
+	rs.nstages = (rhi + 2 - rlo) / RSK + 1;
 
 	// the descriptor slot is reused (see map_slot in resize_fast.cu); lane 0 of any warp may issue a refill
 	if ((tid & 31) == 0) asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(smap) : "memory");
@@ -460,7 +484,6 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// lanes read consecutive words and, in the emit, write consecutive float4s: no bank conflicts).
 	const uint32_t thread_off = DEEP ? 8 * tid : 4 * tid;
 	uint32_t faddr = 0;     // shared address of this thread's first chunk in the next row to fetch
-	int fleft = 0;          // rows left to fetch in the current stage
 	auto load_row = [&](uint32_t (&w)[WPT]) {
 		if (DEEP) {
 #pragma unroll
@@ -476,7 +499,6 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	};
 	auto advance = [&]() {
 		rs = ring_advance<DEEP>(smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
-		fleft = RSK;
 		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
 	};
 
@@ -499,8 +521,13 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 
 	// One source row into every open output row.  The value is used as the subnormal float its bits
 	// already are (see the header); weights come from the constant bank as uniform operands.
-	auto body = [&](const uint32_t (&cur)[WPT], const float (&w)[DEPTH]) {
-#if PICHA_DOWN_PACKED
+	auto body = [&](const uint32_t (&cur)[WPT], const float (&w)[DEPTH + 1]) {
+#ifdef PICHA_DOWN_SKIP_BODY      // (timing experiments only: the row loop without its arithmetic)
+		uint32_t x = __float_as_uint(w[0]);
+#pragma unroll
+		for (int i = 0; i < WPT; ++i) x ^= cur[i];
+		acc[0][0] ^= x;
+#elif PICHA_DOWN_PACKED
 #pragma unroll
 		for (int i = 0; i < NV; i += 2) {
 			uint32_t b0, b1;
@@ -524,9 +551,9 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	};
 	// The weights of a row are fetched from the constant bank into uniform registers one row ahead,
 	// like the data: issued right in front of their first use, the load's latency stalls every row.
-	auto load_w = [&](float (&w)[DEPTH], int widx) {
+	auto load_w = [&](float (&w)[DEPTH + 1], int widx) {
 #pragma unroll
-		for (int j = 0; j < DEPTH; ++j) w[j] = vt.wt[widx + j];
+		for (int j = 0; j <= DEPTH; ++j) w[j] = vt.wt[widx + j];     // [DEPTH]: the row's event flags
 	};
 
 	Pass2Args pa;
@@ -535,93 +562,115 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * BPP;
 	const uint32_t my_tmp = sbase + L.tmp + tid * 16;
 
+	// The row loop.  Which rows complete an output is not computed here: the host has put the number of outputs
+	// a row completes (and whether the ring stage ends with the next row: bands start on stage boundaries) into
+	// a flag word behind the row's weights.  The weights of a row are fetched a row ahead, so the flag has been in a uniform
+	// register for a whole row body when the branch at the end of the body needs it -- all the loop decides per
+	// row is "did this row complete something" and "is the ring stage used up", both on values known long before.
+	// (The first version walked per-output row counts from a table: the chain table load -> min -> counters ->
+	// slot comparison -> branches sat on the critical path of every output, ~300 cycles of fixed latency that
+	// three warps per scheduler cannot hide; measured, the row loop ran at 160 cycles per row against 89 for the
+	// row body alone.)  The output loop is unrolled DEPTH times: the slot of every emit is static.
 	uint32_t ra[WPT], rb[WPT];
-	float wa[DEPTH], wb[DEPTH];
+	float wa[DEPTH + 1], wb[DEPTH + 1];
 	advance();
 	load_row(ra);
-	--fleft;
-	int y = vt.band_ys[band];                      // oldest open output row
-	int yslot = y % DEPTH;
-	int widx = (rlo - vt.row_base) * WS;           // weights of the row after the one held in ra
+	int widx = (rlo - vt.row_base) * WS;           // weights of the row held in ra, then of the one after it
 	load_w(wa, widx);
 	widx += WS;
+	// outputs are taken in rounds of DEPTH starting at slot 0: the band's oldest open output is preceded by the
+	// (up to DEPTH - 1) outputs that share its round; they count as complete before the first row and are discarded
+	const int ys = vt.band_ys[band];
+	int y = ys - ys % DEPTH;
+	int pending = ys - y;                          // outputs complete and not yet emitted
 	int gcount = 0;
-	// ytab holds, per output row, how many more source rows complete it once the previous output is complete
-	// (the band's first output counts from the band's first row instead: band_n0); fetched one output ahead
-	int tix = y - vt.out_base + 1;
-	int n_next = vt.band_n0[band];
-	while (y < y1) {
-		int n = n_next;                            // output y is complete after this many more rows
-		n_next = vt.ytab[tix];
-		++tix;
-		while (n > 0) {
-			if (fleft == 0) advance();
-			int m = min(n, fleft);
-			n -= m;
-			fleft -= m;
-			do {
-				load_row(rb);
-				load_w(wb, widx);
-				body(ra, wa);
-				widx += WS;
-				if (--m == 0) {
+	auto flags = [](const float (&w)[DEPTH + 1]) { return (int)__float_as_uint(w[DEPTH]); };
+	bool done = y >= y1;
+	while (!done) {
 #pragma unroll
-					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+		for (int s = 0; s < DEPTH; ++s) {
+			if (done) break;
+			if (pending == 0) {
+				for (;;) {
+					load_row(rb);
+					load_w(wb, widx);
+					widx += WS;
+					body(ra, wa);
+					int f = flags(wa);
+					if (f) {
+						// (rare path: once per output and once per ring stage) continue with the current row in ra
 #pragma unroll
-					for (int j = 0; j < DEPTH; ++j) wa[j] = wb[j];
-					break;
-				}
-				load_row(ra);
-				load_w(wa, widx);
-				body(rb, wb);
-				widx += WS;
-			} while (--m);
-		}
-		// emit: slot y % DEPTH is final; it becomes the slot of output y + DEPTH
+						for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
 #pragma unroll
-		for (int j = 0; j < DEPTH; ++j) {
-			if (j == yslot) {
-				if (y >= y0) {
-#if PICHA_DOWN_PACKED
-#pragma unroll
-					for (int q = 0; q < 4; ++q) {
-						float4 v;
-						unpair(acc[j][2 * q], v.x, v.y);
-						unpair(acc[j][2 * q + 1], v.z, v.w);
-						sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
+						for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+						if (f & kEvStage) advance();
+						pending = f & kEvCount;
+						if (pending) break;
+						continue;
 					}
-#else
-#pragma unroll
-					for (int q = 0; q < 4; ++q)
-						sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024,
-						    make_float4(acc[j][4 * q], acc[j][4 * q + 1], acc[j][4 * q + 2], acc[j][4 * q + 3]));
-#endif
-					++gcount;
+					load_row(ra);
+					load_w(wa, widx);
+					widx += WS;
+					body(rb, wb);
+					f = flags(wb);
+					if (f) {
+						if (f & kEvStage) advance();
+						pending = f & kEvCount;
+						if (pending) break;
+					}
 				}
-				// in place (tied operand, x * 0): a plain "= 0.0f" makes new values that ptxas pairs up for CS2R and
-				// then shuffles every accumulator of the kernel between two register assignments per output row
+			}
+			// emit: slot s is final; it becomes the slot of output y + DEPTH
+			if (y >= y0) {
 #if PICHA_DOWN_PACKED
 #pragma unroll
-				for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[j][i]) : "l"(0ull));
+				for (int q = 0; q < 4; ++q) {
+					float4 v;
+					unpair(acc[s][2 * q], v.x, v.y);
+					unpair(acc[s][2 * q + 1], v.z, v.w);
+					sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
+				}
 #else
 #pragma unroll
-				for (int i = 0; i < NV; ++i) asm volatile("mul.f32 %0, %0, 0f00000000;" : "+f"(acc[j][i]));
+				for (int q = 0; q < 4; ++q)
+					sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024,
+					    make_float4(acc[s][4 * q], acc[s][4 * q + 1], acc[s][4 * q + 2], acc[s][4 * q + 3]));
 #endif
+				++gcount;
 			}
-		}
-		++y;
-		if (++yslot == DEPTH) yslot = 0;
-		if (gcount == GR || (y == y1 && gcount > 0)) {
-			pa.ng = gcount;
-			pa.gbase = dtile + (long long)(y - gcount) * dst.stride;
-			__syncthreads();           // the group's intermediate rows are complete
-			pass2<C, DEEP, GR>(pa);
-			__syncthreads();           // pass 1 may overwrite the intermediate rows again
-			gcount = 0;
+			// in place (tied operand, x * 0): a plain "= 0.0f" makes new values that ptxas pairs up for CS2R and
+			// then shuffles every accumulator of the kernel between two register assignments per output row
+#if PICHA_DOWN_PACKED
+#pragma unroll
+			for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[s][i]) : "l"(0ull));
+#else
+#pragma unroll
+			for (int i = 0; i < NV; ++i) asm volatile("mul.f32 %0, %0, 0f00000000;" : "+f"(acc[s][i]));
+#endif
+			--pending;
+			++y;
+			done = y >= y1;
+			if (gcount == GR || (done && gcount > 0)) {
+				pa.ng = gcount;
+				pa.gbase = dtile + (long long)(y - gcount) * dst.stride;
+#ifndef PICHA_DOWN_SKIP_SYNC     // (timing experiments only)
+				__syncthreads();           // the group's intermediate rows are complete
+#endif
+#ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
+				pass2<C, DEEP, GR>(pa);
+#endif
+#ifndef PICHA_DOWN_SKIP_SYNC
+				__syncthreads();           // pass 1 may overwrite the intermediate rows again
+#endif
+				gcount = 0;
+			}
 		}
 	}
 
 	// Never leave with a TMA load still in flight: wait for every stage that was issued.
+#ifdef PICHA_DOWN_NO_REFILL
+	rs.stage = rs.nstages;
+#endif
 	for (int k = rs.stage + 1; k < rs.nstages && k < rs.stage + NS; ++k) {
 		if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
 		fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);

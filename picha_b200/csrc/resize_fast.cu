@@ -24,6 +24,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -149,6 +150,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		float wmax = 0;
 		for (float w : fy.wv) wmax = std::fmax(wmax, std::fabs(w));
 		if (!(wmax < 128.0f)) use_down = false;      // weights carry 2^120 in that kernel
+		for (int d : fy.done)
+			if (d > (int)down::kEvCount) use_down = false;   // the row loop's event flag counts to 7
 		dl.da.nb = (channels & 1) ? (channels * t.xtaps + 3 + 4 * channels - 1) / (4 * channels) : (t.xtaps + 3) / 4;
 		// few distinct weight rows (integer and small p/q ratios): the tile keeps just those
 		const int rows = (channels & 1) ? t.xe_count[channels == 3] : t.xunique;
@@ -240,7 +243,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, tall strips (little
 	// vertical halo) when it is large; multiples of 8 rows; small enough that one band's vertical
 	// tables fit a launch's parameter block.
-	const int WS = (depth + 3) & ~3;
+	const int WS = use_down ? down::weight_stride(depth) : (depth + 3) & ~3;   // floats per row of the vertical table
 	const int dh = dst.height;
 	const int ctas_per_sm = use_down || use_up ? 6 : 4;
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
@@ -252,9 +255,13 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	if (want > max_bands) want = max_bands;
 	if (want < 1) want = 1;
 	int band_h = (int)(((dh + want - 1) / want + 7) / 8 * 8);
+	// The downscaling kernel starts every band on a ring-stage boundary (a multiple of `rsk` source rows): its row
+	// loop learns where stages end from a flag in the weight table, which is shared by all bands of a launch.
+	const int rsk = use_down ? down::stage_rows(deep) : 1;
+	auto first_row = [&](int y0) { return fy.smin[y0] & ~(rsk - 1); };
 	auto band_fits = [&](int y0, int y1) {
-		const int rows = fy.cum[y1 - 1] - fy.smin[y0] + 1;
-		const int outs = fy.variant == 0 ? y1 - fy.ybase[fy.smin[y0]] : y1 - y0;
+		const int rows = fy.cum[y1 - 1] - first_row(y0) + 1;
+		const int outs = fy.variant == 0 ? y1 - fy.ybase[first_row(y0)] : y1 - y0;
 		// (the downscaling kernel reads the weights one row ahead and may start up to depth - 1 outputs early)
 		return outs + kFastMaxDepth <= kYtabMax && ((fy.variant == 0 ? rows : outs) + 1) * WS <= kWtMax;
 	};
@@ -289,14 +296,14 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		if (bands == 0) return cudaErrorNotSupported;
 		vt.y_begin = yb;
 		vt.y_end = ye;
-		const int row_lo = fy.smin[yb], row_hi = fy.cum[ye - 1];
+		const int row_lo = first_row(yb), row_hi = fy.cum[ye - 1];
 		vt.row_base = row_lo;
 		vt.out_base = fy.variant == 0 ? fy.ybase[row_lo] : yb;
 		for (int b = 0; b < bands; ++b) {
 			const int y0 = yb + b * band_h, y1 = std::min(ye, y0 + band_h);
-			vt.band_rlo[b] = fy.smin[y0];
+			vt.band_rlo[b] = first_row(y0);
 			vt.band_rhi[b] = fy.cum[y1 - 1];
-			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[fy.smin[y0]] : y0;
+			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[first_row(y0)] : y0;
 			vt.band_n0[b] = fy.variant == 0 ? fy.cum[vt.band_ys[b]] - vt.band_rlo[b] + 1 : 0;
 		}
 		const int *ysrc = fy.variant == 0 || use_up ? fy.cum.data() : fy.lo.data();
@@ -316,6 +323,10 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				float *w = vt.wt + (i - first) * WS;
 				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
 				for (int j = 0; j < fy.depth; ++j) w[(fy.ybase[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale;
+				// the row loop's event flags: how many outputs this row completes, and whether the row after it is the
+				// last of its ring stage
+				const uint32_t bits = (uint32_t)fy.done[i] | ((i & (rsk - 1)) == rsk - 2 ? down::kEvStage : 0u);
+				memcpy(&w[depth], &bits, 4);
 			}
 		} else if (use_up) {
 			// slot order: source row r sits in window slot r % depth; scaled so the result lands on [0, 1]

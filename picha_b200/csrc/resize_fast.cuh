@@ -176,6 +176,12 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap *m
 		::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// The same box, only as far as L2: issued a few stages ahead of the copy into shared memory, so that copy finds its
+// rows in L2 (the ring in shared memory is too shallow to cover HBM latency under load; L2 is not).
+__device__ __forceinline__ void tma_prefetch_3d_a(const CUtensorMap *map, int x, int y, int z) {
+	asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
 // Stage transition of the ring, out of line: it runs once per 8 rows, and inlined into every copy of
 // the unrolled row body it would triple the size of the hot loop (instruction-cache misses showed
 // up as the top stall).  Issues stage `issue` (if >= 0) into its slot and waits for `wait_bar`.

@@ -157,6 +157,8 @@ void build_fast_y(const AxisTable &t, int max_depth, FastAxisY &f) {
 		while (y < n && f.cum[y] < r) ++y;
 		f.ybase[r] = y;
 	}
+	f.done.assign(t.src_size + 8, 0);
+	for (int y = 0; y < n; ++y) ++f.done[f.cum[y]];
 	int need_down = 0, need_up = 0;
 	for (int y = 0; y < n; ++y) {
 		for (int k = pk0[y]; k < pk1[y]; ++k) {

@@ -54,6 +54,7 @@ struct FastAxisY {
 	std::vector<int> smin;   // [dst] first effective row touched by any output >= y
 	std::vector<int> ybase;  // [src] kDown: first output still open when row r is consumed
 	std::vector<int> lo;     // [dst] kUp: window base (= smin)
+	std::vector<int> done;   // [src + 8] kDown: how many outputs are complete once row r is consumed (cum[y] == r)
 	std::vector<float> wv;
 };
 void build_fast_y(const AxisTable &y, int max_depth, FastAxisY &out);
