@@ -21,5 +21,6 @@ def launch_count():
 
 
 def last_resize_kernel():
-    """1 bit-exact, 2 generic throughput, 3 / 4 downscaling (4- / 8-row groups), 5 upscaling kernel."""
+    """1 bit-exact, 2 generic throughput, 3 / 4 downscaling (4- / 8-row groups), 5 upscaling kernel,
+    6 downscaling with the integer-ratio horizontal pass (4-channel pixels at 2:1, 3:1, 4:1)."""
     return lib.picha_b200_last_resize_kernel()

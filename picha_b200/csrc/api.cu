@@ -298,6 +298,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	p->ft.xw = fb + o_fxw; p->ft.xstride = fx.stride;
 	p->ft.xtaps = fx.taps;
 	p->ft.h_xfirst = fx.first.data(); p->ft.h_xcount = fx.count.data(); p->ft.h_xw = fx.w.data();
+	p->ft.h_xrow = fx.urow.data();
 	p->ft.xrow = ib + o_fxrow; p->ft.xuw = fb + o_fxuw; p->ft.xunique = fx.unique;
 	for (int ci = 0; ci < 2; ++ci) {
 		p->ft.xe_col[ci] = ib + o_ecol[ci]; p->ft.xe_src[ci] = ib + o_esrc[ci]; p->ft.xe_off[ci] = ib + o_eoff[ci];

@@ -57,7 +57,7 @@ struct FastTables {
 	const int *xe_col[2], *xe_src[2], *xe_off[2];
 	int xe_count[2];
 	// host copies of xfirst / xcount / xw (launch planning; never dereferenced on the device)
-	const int *h_xfirst, *h_xcount;
+	const int *h_xfirst, *h_xcount, *h_xrow;
 	const float *h_xw;
 	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with

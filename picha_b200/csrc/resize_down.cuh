@@ -111,12 +111,42 @@ __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, in
 	return L;
 }
 
+// ---- integer-ratio horizontal pass (4-channel pixels) ------------------------------------------
+// A thread produces 4 neighbouring output pixels of one row from one window of source pixels (a 16-byte unit
+// each): with rq source pixels per output the windows of neighbours overlap, so each unit is loaded once and
+// feeds up to 4 outputs.  The intermediate row is stored with one unit of padding after every 4 * rq units,
+// counted from the first block's nominal window start: the 8 lanes of a shared-memory phase then work on 8
+// neighbouring blocks of the same row, (4 rq + 1) units apart -- an odd distance, so never a bank conflict --
+// and every offset inside a block's window is an immediate.
+constexpr int kIntU = 4;                          // outputs per thread
+constexpr int kIntGuard = 128;                    // zeroed bytes in front of the first row (edge windows start before it)
+constexpr int kIntRowBytes = 16 * (256 + 32 + 4); // units of a row + padding units (rq >= 2) + slack
+constexpr int kIntTabs = 6;                       // weight tables: regular blocks, 2 left-edge blocks, 3 right-edge blocks
+__host__ __device__ constexpr int int_tab_bytes(int nw) { return kIntU * ((nw + 3) & ~3) * 4 + 16; }
+
+struct SmemLayoutInt {
+	int ring, tmp, wtab, bars, total;
+};
+__host__ __device__ inline SmemLayoutInt smem_layout_int(int nw) {
+	SmemLayoutInt L;
+	L.ring = 0;
+	L.tmp = L.ring + NS * STAGE_BYTES;
+	L.wtab = L.tmp + kIntGuard + 4 * kIntRowBytes + 1024;   // 1 KB zeroed tail: the last block's window may end behind the row
+	L.bars = (L.wtab + kIntTabs * int_tab_bytes(nw) + 7) & ~7;
+	L.total = L.bars + 2 * NS * 8;
+	return L;
+}
+
 struct DownArgs {
 	float xscale;   // factor on the horizontal weights: 2^(149 - kVExp) / max
 	int nb;         // blocks every column's horizontal pass runs: 4 taps each (even channel counts), 4 * C floats (odd)
 	int direct;     // destination aligned to the pixel's store unit: pixels are stored from registers (no output tile)
 	int wrows;      // weight rows in shared memory: FastTables::xunique (shared by all columns) or tile_w (one each)
 	int uniq;       // which of the two
+	// integer-ratio horizontal pass (pass2_int4; kernels instantiated with P2 = 1)
+	int rq, dx;     // source pixels per output pixel; taps per output <= rq * dx
+	int off0;       // nominal first tap of column x is rq * x + off0
+	int nl, br0;    // blocks of 4 columns below nl and from br0 on are irregular (image edges): own weight tables
 };
 
 __device__ __forceinline__ void mbar_init_a(uint32_t bar, int count) {
@@ -391,12 +421,106 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 	if (!a.direct) copy_out<BPP>(a);
 }
 
+// ---- pass 2 for integer ratios, 4-channel pixels (see smem_layout_int) ---------------------------
+struct Pass2IntArgs {
+	uint32_t row0;       // shared address of unit 0 of the group's first intermediate row
+	uint32_t wtab;       // shared address of the weight tables
+	uint8_t *gbase;      // destination of the group's first row, at the tile's first column
+	int dstride, tw, ng, tid;
+	int c0;              // nominal first unit of the tile's first block, relative to the tile origin (may be negative)
+	int blk0;            // the tile's first block in the image (x0 / 4)
+	int nl, br0;         // DownArgs
+	int vec;             // destination rows are 16-byte aligned: a block leaves as 16-byte stores
+};
+
+// RQ source pixels per output pixel, at most RQ * DX taps per output.  Lanes: 8 neighbouring blocks x 4 rows.
+template <bool DEEP, int RQ, int DX>
+__device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
+	constexpr int U = kIntU, NW = RQ * DX, NWP = (NW + 3) & ~3, PER = U * RQ, NK = (U - 1) * RQ + NW;
+	constexpr int BPP = 4 * Depth<DEEP>::bytes;
+	const int nblk = (a.tw + U - 1) / U;
+	const int lane = a.tid & 31, g = lane >> 3;
+	for (int i = (a.tid >> 5) * 8 + (lane & 7); i < nblk; i += (NT / 32) * 8) {
+		if (g >= a.ng) continue;
+		const int b = a.blk0 + i;
+		const int slot = b < a.nl ? 1 + b : b >= a.br0 ? 3 + min(b - a.br0, 2) : 0;
+		const uint32_t wt = a.wtab + slot * int_tab_bytes(NW);
+		const uint32_t v = a.row0 + g * kIntRowBytes + 16 * ((PER + 1) * i + a.c0);
+		u64 acc[U][2];
+#pragma unroll
+		for (int u = 0; u < U; ++u) acc[u][0] = acc[u][1] = 0;
+		float4 wq[U];
+#pragma unroll
+		for (int k = 0; k < NK; ++k) {
+			u64 p01, p23;
+			lds_2x64(v + 16 * (k + k / PER), p01, p23);
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int wi = k - u * RQ;       // tap of output u this unit is (compile-time)
+				if (wi < 0 || wi >= NW) continue;
+				if ((wi & 3) == 0) wq[u] = lds<float4>(wt + (u * NWP + wi) * 4);
+				const float w = (wi & 3) == 0 ? wq[u].x : (wi & 3) == 1 ? wq[u].y : (wi & 3) == 2 ? wq[u].z : wq[u].w;
+				ffma2(acc[u][0], p01, pair(w, w));
+				ffma2(acc[u][1], p23, pair(w, w));
+			}
+		}
+		uint32_t px[U][DEEP ? 2 : 1];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			float f[4];
+			unpair(acc[u][0], f[0], f[1]);
+			unpair(acc[u][1], f[2], f[3]);
+			uint32_t pv[4];
+#pragma unroll
+			for (int ch = 0; ch < 4; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
+			if (DEEP) {
+				px[u][0] = __byte_perm(pv[0], pv[1], 0x5410);
+				px[u][DEEP ? 1 : 0] = __byte_perm(pv[2], pv[3], 0x5410);
+			} else {
+				px[u][0] = __byte_perm(__byte_perm(pv[0], pv[1], 0x0040), __byte_perm(pv[2], pv[3], 0x0040), 0x5410);
+			}
+		}
+		uint8_t *gp = a.gbase + (long long)g * a.dstride + (long long)(U * i) * BPP;
+		if (a.vec && U * i + U <= a.tw) {
+			if (DEEP) {
+				reinterpret_cast<uint4 *>(gp)[0] = make_uint4(px[0][0], px[0][DEEP ? 1 : 0], px[1][0], px[1][DEEP ? 1 : 0]);
+				reinterpret_cast<uint4 *>(gp)[1] = make_uint4(px[2][0], px[2][DEEP ? 1 : 0], px[3][0], px[3][DEEP ? 1 : 0]);
+			} else {
+				*reinterpret_cast<uint4 *>(gp) = make_uint4(px[0][0], px[1][0], px[2][0], px[3][0]);
+			}
+		} else {
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				if (U * i + u >= a.tw) break;
+				if (DEEP) reinterpret_cast<uint2 *>(gp)[u] = make_uint2(px[u][0], px[u][DEEP ? 1 : 0]);
+				else reinterpret_cast<uint32_t *>(gp)[u] = px[u][0];
+			}
+		}
+	}
+}
+
+template <bool DEEP> __device__ __forceinline__ void pass2_int4_any(const Pass2IntArgs &a, int rq, int dx) {
+	switch (rq * 8 + dx) {
+		case 2 * 8 + 2: pass2_int4<DEEP, 2, 2>(a); break;
+		case 2 * 8 + 4: pass2_int4<DEEP, 2, 4>(a); break;
+		case 2 * 8 + 6: pass2_int4<DEEP, 2, 6>(a); break;
+		case 3 * 8 + 2: pass2_int4<DEEP, 3, 2>(a); break;
+		case 3 * 8 + 4: pass2_int4<DEEP, 3, 4>(a); break;
+		case 3 * 8 + 6: pass2_int4<DEEP, 3, 6>(a); break;
+		case 4 * 8 + 2: pass2_int4<DEEP, 4, 2>(a); break;
+		case 4 * 8 + 4: pass2_int4<DEEP, 4, 4>(a); break;
+		default: pass2_int4<DEEP, 4, 6>(a); break;
+	}
+}
+
 // ---- the kernel -------------------------------------------------------------------------------
 #ifndef PICHA_DOWN_MINB
 #define PICHA_DOWN_MINB(D) ((D) <= 4 ? 6 : (D) <= 6 ? 5 : 4)
 #endif
 
-template <int DEPTH, bool DEEP, int C, int GR>
+// P2: 0 = general horizontal pass (pass2), 1 = integer-ratio pass for 4-channel pixels (pass2_int4).  A template
+// parameter so that each kernel links one family of callees (the registers of the row loop are what is left over).
+template <int DEPTH, bool DEEP, int C, int GR, int P2>
 #ifndef PICHA_DOWN_MINB8
 #define PICHA_DOWN_MINB8 4
 #endif
@@ -420,9 +544,10 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 
 	const bool direct = da.direct != 0;
 	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct);
+	const SmemLayoutInt LI = smem_layout_int(da.rq * da.dx);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
-	const uint32_t bars = sbase + L.bars;          // full[NS] mbarriers, then NS hand-back mbarriers
+	const uint32_t bars = sbase + (P2 ? LI.bars : L.bars);   // full[NS] mbarriers, then NS hand-back mbarriers
 	const uint32_t ring = sbase + L.ring;
 
 	RingState rs;
@@ -451,6 +576,25 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// this tile's horizontal tables -> shared memory: weights scaled and duplicated (packed-FMA operands)
 	const bool uniq = da.uniq != 0;                // the plan's distinct rows, else one row per column
 	const int wrows = uniq ? da.wrows : tw;
+	// integer-ratio pass: nominal first unit of the tile's first block relative to the tile origin
+	const int c0 = da.rq * x0 + da.off0 - sx0;
+	if (P2) {
+		// weight tables [table][output of the block][tap], zero where a column has no tap: table 0 from a regular
+		// block, 1..2 the image's first blocks, 3..5 its last ones
+		const int nw = da.rq * da.dx, nwp = (nw + 3) & ~3;
+		for (int i = tid; i < kIntTabs * kIntU * nwp; i += NT) {
+			const int tab = i / (kIntU * nwp), u = (i / nwp) % kIntU, j = i % nwp;
+			const int blk = tab == 0 ? da.nl : tab <= 2 ? tab - 1 : da.br0 + (tab - 3);
+			const int x = kIntU * blk + u;
+			float w = 0.0f;
+			if (x < dst.width && j < nw) {
+				const int k = j - (t.xfirst[x] - (da.rq * x + da.off0));
+				if (k >= 0 && k < t.xcount[x]) w = t.xw[(long long)x * t.xstride + k] * da.xscale;
+			}
+			sts(sbase + LI.wtab + tab * int_tab_bytes(nw) + (u * nwp + j) * 4, w);
+		}
+		for (int i = tid; i < (kIntGuard + 4 * kIntRowBytes + 1024) / 4; i += NT) sts(sbase + LI.tmp + 4 * i, 0.0f);
+	} else
 	if (C & 1) {
 		constexpr int ci = C == 3;
 		const int nfl = 4 * flat_chunks(C, da.nb);
@@ -470,14 +614,14 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
 		}
 	}
-	for (int i = tid; i < tw; i += NT) {
+	for (int i = tid; i < (P2 ? 0 : tw); i += NT) {
 		// {byte offset of the column's first (aligned) float in a row, byte offset of its weight row | misalignment}
 		const int first = (t.xfirst[x0 + i] - sx0) * C, off = (C & 1) ? first & 3 : 0;
 		const int wrow = !uniq ? i : (C & 1) ? t.xe_col[C == 3][x0 + i] : t.xrow[x0 + i];
 		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"((first - off) * 4), "r"(wrow * L.xs2 * 4 + off) : "memory");
 	}
 	// padded taps multiply whatever lies behind a column's window by zero: make sure that is never a NaN
-	for (int i = tid; i < L.tmp_floats; i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
+	for (int i = tid; i < (P2 ? 0 : L.tmp_floats); i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
 	__syncthreads();
 
 	// This thread's share of a staged row: four chunks of 4 values, 256 values apart (consecutive
@@ -561,6 +705,21 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
 	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * BPP;
 	const uint32_t my_tmp = sbase + L.tmp + tid * 16;
+	// integer-ratio pass: where this thread's four units of an intermediate row go (one unit of padding after every
+	// 4 * rq units, counted from c0)
+	uint32_t epos[4];
+	Pass2IntArgs pi;
+	if (P2) {
+		const int per = kIntU * da.rq;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int u = tid + NT * q, d = u - c0;
+			epos[q] = sbase + LI.tmp + kIntGuard + 16 * (u + (d >= 0 ? d / per : -1));
+		}
+		pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
+		pi.c0 = c0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
+		pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
+	}
 
 	// The row loop.  Which rows complete an output is not computed here: the host has put the number of outputs
 	// a row completes (and whether the ring stage ends with the next row: bands start on stage boundaries) into
@@ -621,6 +780,10 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 				}
 			}
 			// emit: slot s is final; it becomes the slot of output y + DEPTH
+#ifdef PICHA_DOWN_SKIP_EMIT      // (timing experiments only)
+			if (y >= y0) ++gcount;
+			if (y == -12345)
+#endif
 			if (y >= y0) {
 #if PICHA_DOWN_PACKED
 #pragma unroll
@@ -628,7 +791,8 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 					float4 v;
 					unpair(acc[s][2 * q], v.x, v.y);
 					unpair(acc[s][2 * q + 1], v.z, v.w);
-					sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
+					if (P2) sts(epos[q] + gcount * kIntRowBytes, v);
+					else sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
 				}
 #else
 #pragma unroll
@@ -657,7 +821,13 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 				__syncthreads();           // the group's intermediate rows are complete
 #endif
 #ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
-				pass2<C, DEEP, GR>(pa);
+				if (P2) {
+					pi.ng = gcount;
+					pi.gbase = pa.gbase;
+					pass2_int4_any<DEEP>(pi, da.rq, da.dx);
+				} else {
+					pass2<C, DEEP, GR>(pa);
+				}
 #endif
 #ifndef PICHA_DOWN_SKIP_SYNC
 				__syncthreads();           // pass 1 may overwrite the intermediate rows again
@@ -696,8 +866,8 @@ struct DownLaunch {
 // (griddepcontrol.launch_dependents at the top of the kernel) -- the partial last wave of each
 // launch would otherwise idle a good part of the GPU.  Every CTA ends with griddepcontrol.wait, so a
 // launch never completes before its predecessor and whatever follows in the stream sees all of them.
-template <int DEPTH, bool DEEP, int C, int GR> cudaError_t launch_group(const DownLaunch &a) {
-	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR>;
+template <int DEPTH, bool DEEP, int C, int GR, int P2> cudaError_t launch_group(const DownLaunch &a) {
+	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2>;
 	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
@@ -714,7 +884,8 @@ template <int DEPTH, bool DEEP, int C, int GR> cudaError_t launch_group(const Do
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
-	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8>(a) : launch_group<DEPTH, DEEP, C, 4>(a);
+	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4>(a);   // (C == 4: no instantiation for other formats)
+	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0>(a) : launch_group<DEPTH, DEEP, C, 4, 0>(a);
 }
 
 template <bool DEEP, int C> cudaError_t launch_depth(const DownLaunch &a) {

@@ -214,7 +214,36 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		dl.group = pairs > 0 && clean * 4 < pairs * 3 ? 8 : 4;
 		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 ? 8 : 4;
 	}
-	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
+	// 4-channel pixels at an integer ratio of 2, 3 or 4: the horizontal pass with a sliding window (pass2_int4).
+	// Every column's taps must lie in its nominal window [rq * x + off0, + rq * dx); columns that differ from the
+	// regular one (clipped windows at the image edges) must fall into the first 2 and last 3 blocks of 4 columns.
+	if (use_down && channels == 4 && dl.da.direct && !getenv("PICHA_B200_NO_P2INT") && dst.width >= 32 && t.tile_w % down::kIntU == 0 &&
+	    src.width % dst.width == 0 && src.width / dst.width >= 2 && src.width / dst.width <= 4) {
+		const int rq = src.width / dst.width, dw = dst.width, xm = dw / 2;
+		const int *xf = t.h_xfirst, *xc = t.h_xcount, *xr = t.h_xrow;
+		const int off0 = xf[xm] - rq * xm;
+		int need = 0;
+		bool ok = off0 >= -8;
+		for (int x = 0; x < dw && ok; ++x) {
+			const int d = xf[x] - (rq * x + off0);
+			if (d < 0) ok = false;
+			need = std::max(need, d + xc[x]);
+		}
+		const int dx = need <= 2 * rq ? 2 : need <= 4 * rq ? 4 : 6;
+		if (need > 6 * rq) ok = false;
+		auto regular = [&](int x) { return xr[x] == xr[xm] && xf[x] == rq * x + off0; };
+		int lo = 0, hi = dw;
+		while (ok && lo < dw && !regular(lo)) ++lo;
+		while (ok && hi > lo && !regular(hi - 1)) --hi;
+		for (int x = lo; x < hi && ok; ++x) ok = regular(x);
+		const int nl = (lo + down::kIntU - 1) / down::kIntU, br0 = hi / down::kIntU, nblk = (dw + down::kIntU - 1) / down::kIntU;
+		if (ok && nl <= 2 && nblk - br0 <= 3 && nl < br0) {
+			dl.da.rq = rq; dl.da.dx = dx; dl.da.off0 = off0; dl.da.nl = nl; dl.da.br0 = br0;
+			dl.group = 4;
+		}
+	}
+	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down && dl.da.rq > 0 ? down::smem_layout_int(dl.da.rq * dl.da.dx).total
+	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
 	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;
 
@@ -373,7 +402,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;
 		*launches += 1;
-		g_last_resize_kernel = use_up ? 5 : use_down ? (dl.group == 8 ? 4 : 3) : 2;
+		g_last_resize_kernel = use_up ? 5 : use_down ? (dl.da.rq > 0 ? 6 : dl.group == 8 ? 4 : 3) : 2;
 		yb = ye;
 	}
 	return cudaSuccess;

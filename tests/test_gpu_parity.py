@@ -307,7 +307,13 @@ def test_resize_kernel_variants(gpu, monkeypatch):
             ("rgba", 1024, 600, 256, 150, "lanczos", 1.0), ("rgb", 1200, 640, 160, 160, "cubic", 0.7),
             ("grey", 999, 777, 333, 111, "mitchel", 1.0), ("greya", 1280, 720, 427, 241, "catmulrom", 1.0),
             ("r16g16b16", 900, 500, 300, 250, "triangle", 1.0), ("r16g16b16a16", 800, 1200, 237, 300, "lanczos", 1.0),
-            ("rgba", 2000, 3000, 250, 1500, "box", 1.0), ("r16", 700, 900, 100, 450, "cubic", 1.0)]
+            ("rgba", 2000, 3000, 250, 1500, "box", 1.0), ("r16", 700, 900, 100, 450, "cubic", 1.0),
+            # integer ratios of 4-channel pixels (sliding-window horizontal pass): 2, 3, 4; narrow and wide filters;
+            # widths that are not multiples of a block or a tile; 16-bit
+            ("rgba", 1000, 333, 500, 111, "cubic", 0.7), ("rgba", 1002, 400, 334, 190, "lanczos", 1.0),
+            ("rgba", 1028, 300, 257, 77, "cubic", 0.7), ("r16g16b16a16", 768, 500, 256, 250, "mitchel", 1.0),
+            ("rgba", 512, 256, 128, 64, "triangle", 1.0), ("r16g16b16a16", 1200, 300, 300, 100, "box", 1.0),
+            ("rgba", 640, 480, 320, 240, "catmulrom", 1.4)]
     for group in ("4", "8", None):
         if group is None:
             monkeypatch.delenv("PICHA_B200_DOWN_G", raising=False)
@@ -318,8 +324,15 @@ def test_resize_kernel_variants(gpu, monkeypatch):
             want = oracle_resize(img, dw, dh, filt, fw)
             got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
             assert_resize_close(got, want, False, ("down", group, pixel, sw, sh, dw, dh, filt, fw))
-            assert P.last_resize_kernel() == {"4": 3, "8": 4}.get(group, P.last_resize_kernel())
-            assert P.last_resize_kernel() in (3, 4)
+            k = P.last_resize_kernel()    # 6: the integer-ratio horizontal pass (4-channel pixels), always 4-row groups
+            assert k == 6 or k == {"4": 3, "8": 4}.get(group, k)
+            assert k in (3, 4, 6)
+            if k == 6:                      # and the general horizontal pass on the same shape
+                monkeypatch.setenv("PICHA_B200_NO_P2INT", "1")
+                got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+                monkeypatch.delenv("PICHA_B200_NO_P2INT")
+                assert P.last_resize_kernel() in (3, 4)
+                assert_resize_close(got, want, False, ("down-general", group, pixel, sw, sh, dw, dh, filt, fw))
     up = [("rgba", 300, 200, 1500, 1700, "mitchel", 1.0), ("r16g16b16a16", 257, 400, 771, 1601, "catmulrom", 1.0),
           ("rgba", 500, 300, 520, 310, "cubic", 1.0), ("r16g16b16a16", 200, 150, 333, 999, "lanczos", 1.5),
           ("rgba", 64, 300, 150, 1800, "triangle", 1.0), ("rgba", 640, 480, 1280, 960, "box", 1.0),
@@ -473,7 +486,7 @@ def test_resize_benchmark_shapes(gpu, cfg):
     want = oracle_resize(img, dw, dh, filt, fw)
     got = P.resizeSync(img, dict(opts, width=dw, height=dh))
     # the kernels the benchmark numbers are about: downscaling (4- / 8-row groups) and upscaling
-    assert P.last_resize_kernel() == {"cfg3": 3, "cfg4": 5, "cfg5": 4}[cfg]
+    assert P.last_resize_kernel() == {"cfg3": 6, "cfg4": 5, "cfg5": 4}[cfg]
     assert_resize_close(got, want, False, cfg)
     if cfg != "cfg4":
         assert_resize_close(P.resizeSync(img, dict(opts, width=dw, height=dh, exact=True)), want, True, cfg)
