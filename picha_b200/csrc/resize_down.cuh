@@ -788,11 +788,8 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 #if PICHA_DOWN_PACKED
 #pragma unroll
 				for (int q = 0; q < 4; ++q) {
-					float4 v;
-					unpair(acc[s][2 * q], v.x, v.y);
-					unpair(acc[s][2 * q + 1], v.z, v.w);
-					if (P2) sts(epos[q] + gcount * kIntRowBytes, v);
-					else sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024, v);
+					const uint32_t addr = P2 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024;
+					asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(acc[s][2 * q]), "l"(acc[s][2 * q + 1]) : "memory");
 				}
 #else
 #pragma unroll
