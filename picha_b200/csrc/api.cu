@@ -100,14 +100,15 @@ struct Plan {
 	FastAxisY fy;               // vertical axis of the fast path (host; sliced into kernel parameters)
 	FastAxisX fx;               // horizontal axis of the fast path (host copy, for launch planning)
 	int fast_tile_w[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int fast_align_px[kNumPixels] = {1, 1, 1, 1, 1, 1, 1, 1};   // tile origins are multiples of this many source pixels
 	~Plan() { if (blob) cudaFree(blob); }
 };
 
-// Smallest pixel count whose byte size is a multiple of 16: tile origins (source TMA boxes) and
-// tile widths (destination vector stores) are multiples of it.
-int align_pixels(int bytes_per_pixel) {
-	int unit = 16;
-	while (unit > 1 && (unit / 2 * bytes_per_pixel) % 16 == 0) unit /= 2;
+// Smallest pixel count whose byte size is a multiple of `quantum` bytes: tile origins (source boxes and bulk
+// copies start on 16-byte boundaries) and tile widths (whole 16-byte destination stores) are multiples of it.
+int align_pixels(int bytes_per_pixel, int quantum = 16) {
+	int unit = quantum;
+	while (unit > 1 && (unit / 2 * bytes_per_pixel) % quantum == 0) unit /= 2;
 	return unit;
 }
 
@@ -278,9 +279,14 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		// Tile widths: multiples of the 16-byte pixel group when the destination is the big side (vector
 		// stores on every tile); when the image shrinks by 2x or more the destination is small, so any
 		// multiple of 4 pixels will do and the source row of the tile can be filled to the brim.
+		// (also what the downscaling kernel's integer-ratio horizontal pass wants: blocks of 4 columns)
 		const int unit = p->x.scale >= 2.0f ? 4 : align_pixels(pi.bytes);
+		// tile origins: 16-byte aligned in the source row.  Bulk copies need that by definition; a tensor-map box of
+		// 32-bit words may nominally start at any word, but a start that is not 16-byte aligned faults on this
+		// part (cudaErrorIllegalInstruction; tried).
+		p->fast_align_px[px] = align_pixels(pi.bytes, 16);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone || !well_conditioned ? 0
-			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, align_pixels(pi.bytes), 512);
+			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, p->fast_align_px[px], 512);
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
@@ -433,7 +439,7 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	if (!(flags & PICHA_B200_EXACT) && (large || (flags & PICHA_B200_FORCE_FAST)) && plan->fast_tile_w[s.pixel] > 0) {
 		FastTables ft = plan->ft;
 		ft.tile_w = plan->fast_tile_w[s.pixel];
-		ft.align_px = align_pixels(pixel_info(s.pixel).bytes);
+		ft.align_px = plan->fast_align_px[s.pixel];
 		e = launch_resize_fast(s, d, n, ft, plan->fy, stream, &launches);
 		if (e == cudaErrorNotSupported) cudaGetLastError();
 	}
