@@ -201,34 +201,50 @@ __device__ __noinline__ RingState ring_advance(const CUtensorMap *map, uint32_t 
 		return rs;
 	}
 #endif
-	if (rs.stage >= 0 && rs.stage + NS < rs.nstages) {
-		__syncwarp();
-		if ((tid & 31) == 0) {
-			// arrive on the stage's hand-back barrier; the state it returns holds the pending count before
-			// this arrival: 1 means every other warp has been here already
-			uint32_t pending;
-			asm volatile(
-				"{\n\t.reg .b64 st;\n\t"
-				"mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
-				"mbarrier.pending_count.b64 %0, st;\n\t}"
-				: "=r"(pending) : "r"(bars + 8 * (NS + prev)) : "memory");
-			if (pending == 1) {
-				fast::mbar_expect_tx_a(bars + 8 * prev, STAGE_BYTES);
-#pragma unroll
-				for (int b = 0; b < BOXES; ++b)
-					fast::tma_load_3d_a(ring + prev * STAGE_BYTES + b * RSK * 1024, map, bars + 8 * prev, word0 + b * 256,
-					                    row0 + (rs.stage + NS) * RSK, img);
-				if (PF > 0 && rs.stage + NS + PF < rs.nstages) {
-#pragma unroll
-					for (int b = 0; b < BOXES; ++b)
-						fast::tma_prefetch_3d_a(map, word0 + b * 256, row0 + (rs.stage + NS + PF) * RSK, img);
-				}
-			}
-		}
+	// Everything below is straight-line code for the whole warp (lane 0 acts through predicates, no divergent
+	// region), and the two barrier operations whose results take long -- the arrival on the hand-back barrier and
+	// the first test of the next stage's full barrier -- are both issued before either result is looked at.
+	const bool hand_back = rs.stage >= 0 && rs.stage + NS < rs.nstages;
+	const uint32_t lane0 = (tid & 31) == 0;
+	uint32_t pending = 0;
+	__syncwarp();
+	if (hand_back) {
+		// arrive on the stage's hand-back barrier; the state it returns holds the pending count before
+		// this arrival: 1 means every other warp has been here already
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t.reg .b64 st;\n\t"
+			"setp.ne.u32 p, %2, 0;\n\t"
+			"@p mbarrier.arrive.shared::cta.b64 st, [%1];\n\t"
+			"@p mbarrier.pending_count.b64 %0, st;\n\t}"
+			: "+r"(pending) : "r"(bars + 8 * (NS + prev)), "r"(lane0) : "memory");
 	}
+	const int issue = rs.stage + NS;
 	++rs.stage;
 	if (++rs.slot == NS) { rs.slot = 0; rs.parity ^= 1; }
-	fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
+	uint32_t ok;
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(ok) : "r"(bars + 8 * rs.slot), "r"(rs.parity) : "memory");
+	if (hand_back) {
+		// the last warp to arrive refills the slot with the stage NS ahead
+		asm volatile(
+			"{\n\t.reg .pred q;\n\t"
+			"setp.eq.u32 q, %0, 1;\n\t"
+			"@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%2], %7;\n\t"
+			"@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%3, {%4, %5, %6}], [%2];\n\t}"
+			::"r"(pending), "r"(ring + prev * STAGE_BYTES), "r"(bars + 8 * prev), "l"(map),
+			  "r"(word0), "r"(row0 + issue * RSK), "r"(img), "r"(STAGE_BYTES) : "memory");
+		if (BOXES == 2)
+			asm volatile(
+				"{\n\t.reg .pred q;\n\t"
+				"setp.eq.u32 q, %0, 1;\n\t"
+				"@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%3, {%4, %5, %6}], [%2];\n\t}"
+				::"r"(pending), "r"(ring + prev * STAGE_BYTES + RSK * 1024), "r"(bars + 8 * prev), "l"(map),
+				  "r"(word0 + 256), "r"(row0 + issue * RSK), "r"(img) : "memory");
+	}
+	if (!ok) fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
 	return rs;
 }
 
