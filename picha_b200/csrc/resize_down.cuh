@@ -372,7 +372,12 @@ template <> struct PixelAcc<1> {
 template <int C, bool DEEP, int GR>
 __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
-	constexpr int U = 4;
+	// pixels in flight per thread: 4 for even channel counts; 2 for odd ones, whose blocks hold twice as many loaded
+	// values (with 4 the kernel needs 236 registers, or spills at the 168 that 6 CTAs per SM allow)
+#ifndef PICHA_DOWN_P2_U
+#define PICHA_DOWN_P2_U ((C & 1) ? 2 : 4)
+#endif
+	constexpr int U = PICHA_DOWN_P2_U;
 	constexpr int GSH = GR == 8 ? 3 : 2;
 	const int total = a.tw * GR;
 	const int g = a.tid & (GR - 1);                // NT is a multiple of GR: the same row for every item

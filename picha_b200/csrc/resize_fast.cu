@@ -201,8 +201,10 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		// counts -- or an odd distance with rows two units apart -- odd channel counts).  When that holds
 		// for few column pairs, groups of 8 rows (one column per phase: never a conflict) are worth their
 		// shared memory.
+		// (measured with 2 pixels in flight per thread for odd channel counts: only 4-channel pixels gain from
+		// 8-row groups; the others lose more to the smaller number of CTAs per SM than to the conflicts)
 		int pairs = 0, clean = 0;
-		if (channels != 2) {
+		if (channels == 4) {
 			const int x1 = std::min(dst.width, t.tile_w);
 			for (int x = 0; x + 1 < x1; x += 2) {
 				const int a0 = (host_xfirst[x] * channels) >> 2, a1 = (host_xfirst[x + 1] * channels) >> 2;
