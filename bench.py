@@ -189,7 +189,7 @@ def time_device_steps(fn, steps, warmup):
     return per, evs[0].elapsed_time(evs[-1])
 
 
-def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_cpu=True, batch=None):
+def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_cpu=True, batch=None, extras=False):
     import numpy as np
     import torch
     import picha_b200 as P
@@ -242,7 +242,22 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
            "clocks": clocks, "images_per_gpu": n}
 
     if with_e2e:
-        res["e2e"] = e2e_resize(w, args, rank, local_rank, src, tag, fwidth)
+        big = key == "cfg5"            # thumbnails: enough images per step for the library to cut chunks of one launch each
+        res["e2e"] = e2e_resize(w, args, rank, local_rank, src, tag, fwidth, batch=min(256, n) if big else None)
+        if extras:
+            ceiling = h2d_ceiling(local_rank)
+            res["e2e"]["h2d_ceiling_gbs_per_gpu"] = ceiling
+            res["e2e"]["frac_of_h2d_ceiling"] = round(res["e2e"]["h2d_gbs_per_gpu"] / ceiling, 3) if ceiling else None
+            if world == 1:
+                pg = e2e_resize(w, args, rank, local_rank, src, tag, fwidth, pinned=False, batch=min(64, n) if big else 16,
+                                steps=max(2, args.steps // 4))
+                res["e2e_pageable"] = {k: pg.get(k) for k in ("value", "unit", "ms_per_step", "images_per_step_per_gpu", "h2d_gbs_per_gpu", "api")}
+                res["call_latency"] = [call_latency(w, src, tag, fwidth, t) for t in (4, 16)]
+            else:
+                barrier()
+                if rank == 0:
+                    res["e2e_sharder"] = sharder_e2e(w, args, src, tag, fwidth, world)
+                barrier()
     if with_cpu and rank == 0 and world == 1:
         res["cpu_baseline"] = cpu_baseline_resize(w, src, dst, args)
     del src, dst
@@ -250,52 +265,160 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     return res
 
 
-def e2e_resize(w, args, rank, local_rank, src, tag, fwidth):
-    """The same metric through picha_b200_resize_batch with pinned HOST buffers: every step copies
-    its inputs host->device and its results device->host inside the timed region."""
-    import numpy as np
+class HostImages:
+    """n copies-by-value of the workload's synthetic images in HOST memory (pinned through the library's allocator,
+    or ordinary pageable numpy memory -- what a Node Buffer is), plus destination buffers, as C-ABI image arrays."""
+
+    def __init__(self, w, src, n, pinned=True):
+        import numpy as np
+        from picha_b200 import _native as N
+        self.N, self.n, self.pinned = N, n, pinned
+        bpp = PIXEL_BYTES[w["pixel"]]
+        sstride, dstride = w["sw"] * bpp, (w["dw"] * bpp + 3) & ~3
+        sbytes, dbytes = sstride * w["sh"], dstride * w["dh"]
+        self.ptrs = []
+        if pinned:
+            hp_src, hp_dst = N.lib.picha_b200_host_alloc(n * sbytes), N.lib.picha_b200_host_alloc(n * dbytes)
+            self.ptrs = [hp_src, hp_dst]
+            if not hp_src or not hp_dst:
+                raise MemoryError("pinned allocation failed")
+            host_src = np.ctypeslib.as_array(ctypes.cast(hp_src, ctypes.POINTER(ctypes.c_ubyte)), shape=(n * sbytes,))
+        else:
+            self.keep = (np.empty(n * sbytes, np.uint8), np.empty(n * dbytes, np.uint8))
+            host_src = self.keep[0]
+            hp_src, hp_dst = self.keep[0].ctypes.data, self.keep[1].ctypes.data
+        distinct = min(n, src.n, 8)
+        for i in range(n):   # the same synthetic images the device batch holds, now in host memory
+            if i < distinct:
+                host_src[i * sbytes:(i + 1) * sbytes].reshape(w["sh"], sstride)[:] = src.image(i).rows()
+            else:
+                host_src[i * sbytes:(i + 1) * sbytes] = host_src[(i % distinct) * sbytes:(i % distinct + 1) * sbytes]
+        pix = N.PIXELS.index(w["pixel"])
+        self.srcs = (N.CImage * n)(*[N.CImage(hp_src + i * sbytes, sstride, w["sw"], w["sh"], pix) for i in range(n)])
+        self.dsts = (N.CImage * n)(*[N.CImage(hp_dst + i * dbytes, dstride, w["dw"], w["dh"], pix) for i in range(n)])
+        self.h2d, self.d2h = n * w["sw"] * w["sh"] * bpp, n * w["dw"] * w["dh"] * bpp
+
+    def free(self):
+        for p in self.ptrs:
+            if p:
+                self.N.lib.picha_b200_host_free(p)
+        self.ptrs = []
+
+
+def e2e_resize(w, args, rank, local_rank, src, tag, fwidth, pinned=True, batch=None, steps=None):
+    """The same metric through picha_b200_resize_batch with HOST buffers: every step copies its inputs
+    host->device and its results device->host inside the timed region."""
     import torch
+    import picha_b200 as P
     from picha_b200 import _native as N
 
-    n = min(args.e2e_batch, src.n)
-    bpp = PIXEL_BYTES[w["pixel"]]
-    sstride, dstride = w["sw"] * bpp, (w["dw"] * bpp + 3) & ~3
-    sbytes, dbytes = sstride * w["sh"], dstride * w["dh"]
-    hp_src = N.lib.picha_b200_host_alloc(n * sbytes)
-    hp_dst = N.lib.picha_b200_host_alloc(n * dbytes)
-    if not hp_src or not hp_dst:
-        return {"value": None, "unit": "Mpix/s", "error": "pinned allocation failed"}
+    n = batch or min(args.e2e_batch, src.n)
+    steps = steps or args.steps
     try:
-        host_src = np.ctypeslib.as_array(ctypes.cast(hp_src, ctypes.POINTER(ctypes.c_ubyte)), shape=(n * sbytes,))
-        for i in range(n):   # the same synthetic images the device batch holds, now in host memory
-            img = src.image(i)
-            host_src[i * sbytes:(i + 1) * sbytes].reshape(w["sh"], sstride)[:] = img.rows()
-        pix = N.PIXELS.index(w["pixel"])
-        srcs = (N.CImage * n)(*[N.CImage(hp_src + i * sbytes, sstride, w["sw"], w["sh"], pix) for i in range(n)])
-        dsts = (N.CImage * n)(*[N.CImage(hp_dst + i * dbytes, dstride, w["dw"], w["dh"], pix) for i in range(n)])
-
+        host = HostImages(w, src, n, pinned)
+    except MemoryError as e:
+        return {"value": None, "unit": "Mpix/s", "error": str(e)}
+    try:
         def step():
-            N.check(N.lib.picha_b200_resize_batch(n, srcs, dsts, tag, fwidth, 0, local_rank))
+            N.check(N.lib.picha_b200_resize_batch(n, host.srcs, host.dsts, tag, fwidth, 0, local_rank))
 
         for _ in range(max(1, min(args.warmup, 3))):
             step()
         torch.cuda.synchronize()
         barrier()
+        l0 = P.launch_count()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()                      # blocking: returns when the results are in host memory
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        launches = (P.launch_count() - l0) // steps
         barrier()
-        ms = max_over_ranks(dt * 1e3 / args.steps)
+        ms = max_over_ranks(dt * 1e3 / steps)
         mpix = sum_over_ranks(n * w["dw"] * w["dh"] / 1e6)
         return {"value": round(mpix / (ms / 1e3), 1), "unit": "Mpix/s",
-                "h2d_bytes_per_step": n * w["sw"] * w["sh"] * bpp, "d2h_bytes_per_step": n * w["dw"] * w["dh"] * bpp,
-                "ms_per_step": round(ms, 3), "images_per_step_per_gpu": n,
-                "api": "picha_b200_resize_batch (C-ABI, pinned host buffers from picha_b200_host_alloc)"}
+                "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
+                "ms_per_step": round(ms, 3), "images_per_step_per_gpu": n, "launches_per_step": launches,
+                "h2d_gbs_per_gpu": round(host.h2d / (ms / 1e3) / 1e9, 1),
+                "api": "picha_b200_resize_batch (C-ABI, " + ("pinned host buffers from picha_b200_host_alloc)" if pinned
+                                                              else "pageable host buffers, staged by the library)")}
     finally:
-        N.lib.picha_b200_host_free(hp_src)
-        N.lib.picha_b200_host_free(hp_dst)
+        host.free()
+
+
+def h2d_ceiling(local_rank, mib=256, copies=8):
+    """The platform's ceiling for the e2e numbers: raw pinned host -> device copies on every rank at once
+    (cudaMemcpyAsync through torch), GB/s per GPU as the max time over ranks sees it."""
+    import torch
+    nbytes = mib << 20
+    hsrc = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    ddst = torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    ddst.copy_(hsrc, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(copies):
+        ddst.copy_(hsrc, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    return round(nbytes * copies / dt / 1e9, 1)
+
+
+def sharder_e2e(w, args, src, tag, fwidth, gpus, per_gpu=16):
+    """One process, every GPU of the box: picha_b200_resize_batch(..., device=-1), the library's own sharder
+    (one host thread per GPU inside the call), pinned host buffers.  Rank 0 only; the other ranks wait."""
+    import torch
+    from picha_b200 import _native as N
+    n = per_gpu * gpus
+    try:
+        host = HostImages(w, src, n, True)
+    except MemoryError as e:
+        return {"value": None, "error": str(e)}
+    try:
+        def step():
+            N.check(N.lib.picha_b200_resize_batch(n, host.srcs, host.dsts, tag, fwidth, 0, -1))
+        step()
+        steps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        return {"value": round(n * w["dw"] * w["dh"] / 1e6 / (ms / 1e3), 1), "unit": "Mpix/s", "ms_per_step": round(ms, 3),
+                "images_per_step": n, "gpus": gpus, "h2d_gbs_total": round(host.h2d / (ms / 1e3) / 1e9, 1),
+                "api": "picha_b200_resize_batch(device=-1): one process, one host thread per GPU inside the library"}
+    finally:
+        host.free()
+
+
+def call_latency(w, src, tag, fwidth, threads, calls=8):
+    """What picha.resize does (src/resize.cc:362-364): one image per call, `threads` calls in flight from as many
+    host threads, ordinary (pageable) buffers.  Median latency of a call and the aggregate rate."""
+    import numpy as np
+    from picha_b200 import _native as N
+    host = HostImages(w, src, threads, pinned=False)
+    lat, errs = [[] for _ in range(threads)], []
+
+    def work(i):
+        try:
+            for c in range(calls + 1):
+                t0 = time.perf_counter()
+                N.check(N.lib.picha_b200_resize(ctypes.byref(host.srcs[i]), ctypes.byref(host.dsts[i]), tag, fwidth))
+                if c:
+                    lat[i].append(time.perf_counter() - t0)
+        except Exception as e:   # pragma: no cover
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    wall = time.perf_counter() - t0
+    if errs:
+        return {"error": errs[0]}
+    flat = sorted(x for l in lat for x in l)
+    return {"threads": threads, "median_ms": round(flat[len(flat) // 2] * 1e3, 3), "p90_ms": round(flat[int(len(flat) * 0.9)] * 1e3, 3),
+            "images_per_s": round(threads * (calls + 1) / wall, 1), "calls": len(flat)}
 
 
 def _cpu_pool_rate(fn, items, threads, passes=2):

@@ -75,19 +75,42 @@ struct PinnedBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// PICHA_B200_DEBUG_GUARD=1 (debugging aid; compute-sanitizer is not available everywhere): every lane buffer sits
+// between two 8 MB guard zones filled with a pattern, checked after each host call -- a kernel that writes outside
+// its destination is reported (last_error) instead of silently corrupting a neighbouring allocation.
+const bool g_debug_guard = getenv("PICHA_B200_DEBUG_GUARD") != nullptr;
+constexpr size_t kGuard = size_t(8) << 20;
+
 struct DeviceBuf {
-	uint8_t *p = nullptr;
+	uint8_t *p = nullptr, *raw = nullptr;
 	size_t cap = 0;
 	int ensure(size_t n) {
 		if (n <= cap) return 0;
-		if (p) cudaFree(p);
-		p = nullptr; cap = 0;
+		if (raw) cudaFree(raw);
+		p = raw = nullptr; cap = 0;
 		size_t want = align_up(n + n / 4, 1 << 20);
-		CU(cudaMalloc((void **)&p, want));
+		const size_t guard = g_debug_guard ? kGuard : 0;
+		CU(cudaMalloc((void **)&raw, want + 2 * guard));
+		if (guard) {
+			CU(cudaMemset(raw, 0xA5, guard));
+			CU(cudaMemset(raw + guard + want, 0xA5, guard));
+		}
+		p = raw + guard;
 		cap = want;
 		return 0;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	// (debug) number of guard bytes that no longer hold the pattern; the stream the buffer is used on must be idle
+	long long guard_damage() const {
+		if (!g_debug_guard || !raw) return 0;
+		std::vector<uint8_t> h(kGuard);
+		long long bad = 0;
+		for (int side = 0; side < 2; ++side) {
+			if (cudaMemcpy(h.data(), side ? raw + kGuard + cap : raw, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+			for (uint8_t b : h) bad += b != 0xA5;
+		}
+		return bad;
+	}
+	void release() { if (raw) cudaFree(raw); p = raw = nullptr; cap = 0; }
 };
 
 // ---- resize plans ------------------------------------------------------------------------
@@ -119,9 +142,9 @@ struct Lane {
 	cudaStream_t stream = nullptr;
 	PinnedBuf hin, hout;
 	DeviceBuf din, dout;
-	// pending copy-out of a staged result (batch pipelining)
-	const picha_b200_image *pending_dst = nullptr;
-	size_t pending_pitch = 0;
+	// pending copy-out of staged results (batch pipelining): images whose rows wait in `hout`
+	struct Pending { const picha_b200_image *dst; size_t offset, pitch; };
+	std::vector<Pending> pending;
 };
 
 struct Device {
@@ -191,14 +214,18 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	uint32_t wbits;
 	memcpy(&wbits, &width, 4);
 	PlanKey key(tag, wbits, sw, sh, dw, dh);
-	std::lock_guard<std::mutex> g(dev->mu);
-	auto it = dev->plans.find(key);
-	if (it != dev->plans.end()) {
-		dev->lru.remove(key);
-		dev->lru.push_front(key);
-		*out = it->second;
-		return 0;
+	{
+		std::lock_guard<std::mutex> g(dev->mu);
+		auto it = dev->plans.find(key);
+		if (it != dev->plans.end()) {
+			dev->lru.remove(key);
+			dev->lru.push_front(key);
+			*out = it->second;
+			return 0;
+		}
 	}
+	// Not cached: the tables are built and uploaded WITHOUT the device's lock (first calls of different shapes on
+	// different threads proceed side by side; two threads building the same shape both finish, one result is kept).
 	std::shared_ptr<Plan> p(new Plan());
 	build_axis(tag, width, sw, dw, p->x);
 	build_axis(tag, width, sh, dh, p->y);
@@ -290,7 +317,23 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
-	CU(cudaMemcpy(p->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+	// The upload must have LANDED before any stream may launch a kernel that reads the tables.  A plain cudaMemcpy
+	// does not promise that for pageable sources -- it may return once the data sits in the driver's staging buffer,
+	// with the DMA to the device still queued (and the queue may hold a 30 MB image upload issued just before on the
+	// calling lane's non-blocking stream, which a kernel launched on that stream then overtakes the tables on).
+	// That was the intermittent cudaErrorIllegalAddress / occasional wrong output of the round-1 fuzz runs: a kernel
+	// reading table memory the copy had not reached yet.  An asynchronous copy on a stream
+	// that is then synchronised is complete when the call returns.
+	if (getenv("PICHA_B200_DEBUG_RACY_UPLOAD")) {   // (A/B evidence only: the round-1 upload, profiles/r02_fault_ab.txt)
+		CU(cudaMemcpy(p->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+	} else {
+		cudaStream_t up = nullptr;
+		CU(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+		cudaError_t ce = cudaMemcpyAsync(p->blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice, up);
+		if (ce == cudaSuccess) ce = cudaStreamSynchronize(up);
+		cudaStreamDestroy(up);
+		if (ce != cudaSuccess) return fail_cuda(ce, "upload of the resize tables");
+	}
 	const int *ib = reinterpret_cast<const int *>(p->blob);
 	const float *fb = reinterpret_cast<const float *>(p->blob);
 	p->t.xfirst = ib + o_xfirst; p->t.xcount = ib + o_xcount; p->t.xstart = ib + o_xstart;
@@ -312,11 +355,22 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	}
 	p->ft.xshort = fx.taps <= 4 ? 4 : (fx.taps <= 8 ? 8 : 0);
 
-	dev->plans[key] = p;
-	dev->lru.push_front(key);
-	while (dev->lru.size() > 64) {   // cudaFree of an evicted blob synchronises the device first
-		dev->plans.erase(dev->lru.back());
-		dev->lru.pop_back();
+	std::vector<std::shared_ptr<Plan>> evicted;   // released (cudaFree: a device-wide synchronisation) after the lock
+	{
+		std::lock_guard<std::mutex> g(dev->mu);
+		auto it = dev->plans.find(key);
+		if (it != dev->plans.end()) {             // another thread was faster: keep its plan
+			evicted.push_back(p);
+			p = it->second;
+		} else {
+			dev->plans[key] = p;
+			dev->lru.push_front(key);
+			while (dev->lru.size() > 64) {
+				auto old = dev->plans.find(dev->lru.back());
+				if (old != dev->plans.end()) { evicted.push_back(old->second); dev->plans.erase(old); }
+				dev->lru.pop_back();
+			}
+		}
 	}
 	*out = p;
 	return 0;
@@ -370,51 +424,53 @@ size_t device_pitch(const picha_b200_image &im) {
 	return align_up((size_t)im.width * pixel_info(im.pixel).bytes, 128);
 }
 
-// Host image -> lane->din (pitch `pitch`), asynchronously on the lane's stream.
-int upload(Lane *lane, const picha_b200_image &im, size_t pitch) {
+// Host image -> lane->din + offset (pitch `pitch`), asynchronously on the lane's stream.  Pinned sources are
+// copied in place (one strided copy); pageable ones are re-pitched into the lane's pinned staging buffer, which the
+// caller then sends with one copy per chunk (flush_uploads).  The buffers have been sized by the caller.
+int upload(Lane *lane, const picha_b200_image &im, size_t pitch, size_t offset, bool *staged) {
 	const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
-	int rc = lane->din.ensure(pitch * im.height);
-	if (rc) return rc;
 	if (row == 0) return 0;
 	if (is_pinned(im.data)) {
-		CU(cudaMemcpy2DAsync(lane->din.p, pitch, im.data, im.stride, row, im.height, cudaMemcpyHostToDevice, lane->stream));
+		CU(cudaMemcpy2DAsync(lane->din.p + offset, pitch, im.data, im.stride, row, im.height, cudaMemcpyHostToDevice, lane->stream));
 		return 0;
 	}
-	rc = lane->hin.ensure(pitch * im.height);
-	if (rc) return rc;
 	const uint8_t *s = static_cast<const uint8_t *>(im.data);
-	for (int y = 0; y < im.height; ++y) memcpy(lane->hin.p + y * pitch, s + (size_t)y * im.stride, row);
-	CU(cudaMemcpyAsync(lane->din.p, lane->hin.p, pitch * im.height, cudaMemcpyHostToDevice, lane->stream));
+	for (int y = 0; y < im.height; ++y) memcpy(lane->hin.p + offset + y * pitch, s + (size_t)y * im.stride, row);
+	*staged = true;
 	return 0;
 }
 
-// lane->dout -> host image (payload bytes only), asynchronously; staged results are copied out
-// by finish().
-int download(Lane *lane, const picha_b200_image &im, size_t pitch) {
+// lane->dout + offset -> host image (payload bytes only), asynchronously; results for pageable destinations go to
+// the lane's pinned buffer (one copy per chunk: flush_downloads) and are copied out by finish().
+int download(Lane *lane, const picha_b200_image &im, size_t pitch, size_t offset, bool *staged) {
 	const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
-	lane->pending_dst = nullptr;
 	if (row == 0) return 0;
 	if (is_pinned(im.data)) {
-		CU(cudaMemcpy2DAsync(im.data, im.stride, lane->dout.p, pitch, row, im.height, cudaMemcpyDeviceToHost, lane->stream));
+		CU(cudaMemcpy2DAsync(im.data, im.stride, lane->dout.p + offset, pitch, row, im.height, cudaMemcpyDeviceToHost, lane->stream));
 		return 0;
 	}
-	int rc = lane->hout.ensure(pitch * im.height);
-	if (rc) return rc;
-	CU(cudaMemcpyAsync(lane->hout.p, lane->dout.p, pitch * im.height, cudaMemcpyDeviceToHost, lane->stream));
-	lane->pending_dst = &im;
-	lane->pending_pitch = pitch;
+	lane->pending.push_back(Lane::Pending{&im, offset, pitch});
+	*staged = true;
 	return 0;
 }
 
 int finish(Lane *lane) {
 	CU(cudaStreamSynchronize(lane->stream));
-	if (lane->pending_dst) {
-		const picha_b200_image &im = *lane->pending_dst;
+	if (g_debug_guard) {
+		const long long a = lane->din.guard_damage(), b = lane->dout.guard_damage();
+		if (a || b) {
+			g_last_error = "PICHA_B200_DEBUG_GUARD: " + std::to_string(a) + " guard bytes around the source buffer and " +
+			               std::to_string(b) + " around the destination buffer were overwritten";
+			return PICHA_B200_ERR_CUDA;
+		}
+	}
+	for (const Lane::Pending &p : lane->pending) {
+		const picha_b200_image &im = *p.dst;
 		const size_t row = (size_t)im.width * pixel_info(im.pixel).bytes;
 		uint8_t *d = static_cast<uint8_t *>(im.data);
-		for (int y = 0; y < im.height; ++y) memcpy(d + (size_t)y * im.stride, lane->hout.p + y * lane->pending_pitch, row);
-		lane->pending_dst = nullptr;
+		for (int y = 0; y < im.height; ++y) memcpy(d + (size_t)y * im.stride, lane->hout.p + p.offset + y * p.pitch, row);
 	}
+	lane->pending.clear();
 	return 0;
 }
 
@@ -477,22 +533,69 @@ struct Op {
 	bool cmyk;                              // convert: the JPEG decoder's cmyk_to_rgb instead of doColorConvert
 };
 
-// One image through one lane: upload, kernel, download (all asynchronous on the lane's stream).
-int submit(Device *dev, Lane *lane, const Op &op, const picha_b200_image &s, const picha_b200_image &d) {
-	const size_t sp = device_pitch(s), dp = device_pitch(d);
-	int rc = upload(lane, s, sp);
-	if (rc) return rc;
-	rc = lane->dout.ensure(dp * d.height);
-	if (rc) return rc;
-	DevBatch sb = dev_batch(lane->din.p, 0, sp, s), db = dev_batch(lane->dout.p, 0, dp, d);
-	rc = op.resize ? run_resize(dev, sb, db, 1, op.tag, op.width, op.flags, lane->stream)
-	               : run_convert(sb, db, 1, op.r, op.g, op.b, lane->stream, op.cmyk);
-	if (rc) return rc;
-	return download(lane, d, dp);
+bool same_shape(const picha_b200_image &a, const picha_b200_image &b) {
+	return a.width == b.width && a.height == b.height && a.pixel == b.pixel;
 }
 
-// A batch on one device: images round-robin over a few lanes so the copy engines and the SMs
-// overlap (H2D of image i+1 with the kernel of image i and the D2H of image i-1).
+// k same-shape images through one lane: uploads, ONE kernel launch over the chunk, downloads (all asynchronous on
+// the lane's stream).
+int submit_chunk(Device *dev, Lane *lane, const Op &op, int k, const picha_b200_image *srcs, const picha_b200_image *dsts) {
+	const picha_b200_image &s = srcs[0], &d = dsts[0];
+	const size_t sp = device_pitch(s), dp = device_pitch(d);
+	const size_t sstep = align_up(sp * s.height, 256), dstep = align_up(dp * d.height, 256);
+	int rc = lane->din.ensure(sstep * k);
+	if (!rc) rc = lane->dout.ensure(dstep * k);
+	bool any_pageable_src = false, any_pageable_dst = false;
+	for (int i = 0; i < k; ++i) {
+		any_pageable_src |= !is_pinned(srcs[i].data);
+		any_pageable_dst |= !is_pinned(dsts[i].data);
+	}
+	if (!rc && any_pageable_src) rc = lane->hin.ensure(sstep * k);
+	if (!rc && any_pageable_dst) rc = lane->hout.ensure(dstep * k);
+	if (rc) return rc;
+	// uploads: staged images form runs of consecutive slots, each sent with one copy
+	int run_begin = -1;
+	auto flush = [&](int end) -> int {
+		if (run_begin < 0) return 0;
+		CU(cudaMemcpyAsync(lane->din.p + sstep * run_begin, lane->hin.p + sstep * run_begin, sstep * (end - run_begin - 1) + sp * s.height,
+		                   cudaMemcpyHostToDevice, lane->stream));
+		run_begin = -1;
+		return 0;
+	};
+	for (int i = 0; i < k; ++i) {
+		bool staged = false;
+		rc = upload(lane, srcs[i], sp, sstep * i, &staged);
+		if (rc) return rc;
+		if (staged && run_begin < 0) run_begin = i;
+		if (!staged && (rc = flush(i))) return rc;
+	}
+	if ((rc = flush(k))) return rc;
+	DevBatch sb = dev_batch(lane->din.p, (int64_t)sstep, sp, s), db = dev_batch(lane->dout.p, (int64_t)dstep, dp, d);
+	rc = op.resize ? run_resize(dev, sb, db, k, op.tag, op.width, op.flags, lane->stream)
+	               : run_convert(sb, db, k, op.r, op.g, op.b, lane->stream, op.cmyk);
+	if (rc) return rc;
+	run_begin = -1;
+	auto flush_down = [&](int end) -> int {
+		if (run_begin < 0) return 0;
+		CU(cudaMemcpyAsync(lane->hout.p + dstep * run_begin, lane->dout.p + dstep * run_begin, dstep * (end - run_begin - 1) + dp * d.height,
+		                   cudaMemcpyDeviceToHost, lane->stream));
+		run_begin = -1;
+		return 0;
+	};
+	for (int i = 0; i < k; ++i) {
+		bool staged = false;
+		rc = download(lane, dsts[i], dp, dstep * i, &staged);
+		if (rc) return rc;
+		if (staged && run_begin < 0) run_begin = i;
+		if (!staged && (rc = flush_down(i))) return rc;
+	}
+	return flush_down(k);
+}
+
+// A batch on one device: runs of same-shape images are cut into chunks, chunks go round-robin over a few lanes
+// so the copy engines and the SMs overlap (H2D of chunk c+1 with the kernel of chunk c and the D2H of chunk c-1).
+// A chunk is one kernel launch, whatever its size (the launch of a single image is a few tiles: it cannot fill
+// the GPU, and a descriptor upload per image costs more than a thumbnail's resize).
 int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *srcs, picha_b200_image *dsts) {
 	Device *dev = get_device(ordinal);
 	if (!dev) { g_last_error = "no such CUDA device"; return PICHA_B200_ERR_NO_DEVICE; }
@@ -506,17 +609,26 @@ int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *sr
 		lanes[l] = dev->acquire();
 		if (!lanes[l]) { rc = PICHA_B200_ERR_CUDA; g_last_error = "cudaStreamCreate failed"; }
 	}
-	for (int i = 0; i < n && !rc; ++i) {
-		const int l = i % kLanes;
+	// chunk size: at least two chunks per lane when the batch allows (overlap), at most 32 images or ~128 MB of source
+	const int by_count = n / (2 * kLanes) > 0 ? n / (2 * kLanes) : 1;
+	int chunk = 0;
+	for (int i = 0; i < n && !rc; ++chunk) {
+		const size_t bytes = align_up(device_pitch(srcs[i]) * srcs[i].height, 256);
+		const int by_bytes = bytes > 0 && (size_t(128) << 20) / bytes > 0 ? (int)((size_t(128) << 20) / bytes) : 1;
+		const int kmax = by_count < by_bytes ? (by_count < 32 ? by_count : 32) : (by_bytes < 32 ? by_bytes : 32);
+		int k = 1;
+		while (i + k < n && k < kmax && same_shape(srcs[i], srcs[i + k]) && same_shape(dsts[i], dsts[i + k])) ++k;
+		const int l = chunk % kLanes;
 		if (busy[l]) { rc = finish(lanes[l]); busy[l] = false; if (rc) break; }
-		rc = submit(dev, lanes[l], op, srcs[i], dsts[i]);
+		rc = submit_chunk(dev, lanes[l], op, k, srcs + i, dsts + i);
 		busy[l] = (rc == 0);
+		i += k;
 	}
 	for (int l = 0; l < kLanes; ++l) {
 		if (!lanes[l]) continue;
 		if (busy[l]) { int r2 = finish(lanes[l]); if (!rc) rc = r2; }
 		else if (rc) cudaStreamSynchronize(lanes[l]->stream);
-		lanes[l]->pending_dst = nullptr;
+		lanes[l]->pending.clear();
 		dev->release(lanes[l]);
 	}
 	return rc;

@@ -101,32 +101,83 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 	return best;
 }
 
-// Device-resident TMA descriptors: one 128-byte slot per resize call from a ring per device.  A slot comes
-// round again after kMapSlots calls, long after the kernels of its previous use have finished; the kernels
-// acquire-fence the tensormap proxy before their first copy so a cached copy of the old contents is not used.
-static std::mutex g_map_mu;
-static std::map<int, std::pair<CUtensorMap *, unsigned>> g_map_rings;   // device -> (ring, next slot)
+// Device-resident TMA descriptors: one 128-byte slot per resize call from a ring per device.  The slot is written
+// on the device, in stream order ahead of the resize launches (a one-warp kernel that takes the encoded descriptor
+// as a parameter), so the consumers' fence.proxy.tensormap::generic.acquire.gpu has the scope the writer needs.
+// A slot's lifetime is explicit: an event recorded behind the last launch that reads it, and waited for (it has
+// long completed, normally) before the slot is handed out again kMapSlots calls later -- callers may run resizes on
+// any number of streams, so "long ago" is not an ordering.
+namespace {
 
-static CUtensorMap *map_slot() {
-	constexpr unsigned kMapSlots = 4096;
+constexpr unsigned kMapSlots = 1024;
+
+struct MapRing {
+	CUtensorMap *slots = nullptr;
+	cudaEvent_t events[kMapSlots] = {};
+	unsigned next = 0;
+};
+std::mutex g_map_mu;
+std::map<int, MapRing *> g_map_rings;   // device -> ring
+
+__global__ void write_descriptor_kernel(CUtensorMap *slot, const __grid_constant__ CUtensorMap map) {
+	const uint64_t *src = reinterpret_cast<const uint64_t *>(&map);
+	uint64_t *dst = reinterpret_cast<uint64_t *>(slot);
+	if (threadIdx.x < sizeof(CUtensorMap) / 8) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// Reserves a slot (waiting for the kernels of its previous use) and returns it with its index.
+CUtensorMap *map_slot(unsigned *index) {
 	int dev = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-	std::lock_guard<std::mutex> lock(g_map_mu);
-	auto it = g_map_rings.find(dev);
-	if (it == g_map_rings.end()) {
-		CUtensorMap *p = nullptr;
-		if (cudaMalloc((void **)&p, kMapSlots * sizeof(CUtensorMap)) != cudaSuccess) return nullptr;
-		it = g_map_rings.emplace(dev, std::make_pair(p, 0u)).first;
+	MapRing *ring;
+	unsigned i;
+	cudaEvent_t ev;
+	{
+		std::lock_guard<std::mutex> lock(g_map_mu);
+		auto it = g_map_rings.find(dev);
+		if (it == g_map_rings.end()) {
+			ring = new MapRing();
+			if (cudaMalloc((void **)&ring->slots, kMapSlots * sizeof(CUtensorMap)) != cudaSuccess) { delete ring; return nullptr; }
+			it = g_map_rings.emplace(dev, ring).first;
+		}
+		ring = it->second;
+		i = ring->next++ % kMapSlots;
+		ev = ring->events[i];
 	}
-	return it->second.first + (it->second.second++ % kMapSlots);
+	if (ev && cudaEventSynchronize(ev) != cudaSuccess) return nullptr;
+	*index = i;
+	return ring->slots + i;
 }
+
+// Behind the last launch that reads the slot.
+cudaError_t map_slot_release(unsigned index, cudaStream_t stream) {
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	cudaEvent_t ev;
+	{
+		std::lock_guard<std::mutex> lock(g_map_mu);
+		MapRing *ring = g_map_rings[dev];
+		if (!ring->events[index]) {
+			e = cudaEventCreateWithFlags(&ring->events[index], cudaEventDisableTiming);
+			if (e != cudaSuccess) return e;
+		}
+		ev = ring->events[index];
+	}
+	return cudaEventRecord(ev, stream);
+}
+
+}  // namespace
 
 // picha_b200_shutdown: the calling thread has selected `device` and synchronised it.
 void release_resize_descriptors(int device) {
 	std::lock_guard<std::mutex> lock(g_map_mu);
 	auto it = g_map_rings.find(device);
 	if (it == g_map_rings.end()) return;
-	cudaFree(it->second.first);
+	for (cudaEvent_t ev : it->second->events)
+		if (ev) cudaEventDestroy(ev);
+	cudaFree(it->second->slots);
+	delete it->second;
 	g_map_rings.erase(it);
 }
 
@@ -194,6 +245,11 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		ul.ua.hscale = std::ldexp(1.0f, up::kHExp);
 		if (up::smem_bytes(ul.ua.win_bytes) > max_dynamic_smem()) use_up = false;
 	}
+	// The generic kernel is not a default route any more: shapes neither specialised kernel takes (vertical depth
+	// above 8; a vertical upscale with a horizontal downscale; misaligned destinations of upscales) get the bit-exact
+	// kernel.  It once failed with an illegal address under a fuzz sequence and the cause was never pinned down
+	// (DESIGN.md section 9); PICHA_B200_GENERIC=1 (and the A/B switch PICHA_B200_OLD_UP) still reach it.
+	if (!use_down && !use_up && !getenv("PICHA_B200_GENERIC") && !getenv("PICHA_B200_OLD_UP")) return cudaErrorNotSupported;
 	if (use_down) {
 		// Rows per pass-2 group.  With 4, the eight lanes that share a shared-memory phase of a float4 read
 		// are four rows of two neighbouring columns; they hit distinct banks only if the columns' windows
@@ -262,15 +318,6 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 	                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) return cudaErrorNotSupported;
-	// The kernels fetch the descriptor from global memory, not from their parameter block (DESIGN 9): a slot
-	// of a per-device ring, written in stream order ahead of the launches.
-	CUtensorMap *dmap = map_slot();
-	if (!dmap) return cudaErrorMemoryAllocation;
-	{
-		cudaError_t ce = cudaMemcpyAsync(dmap, &map, sizeof(map), cudaMemcpyHostToDevice, stream);   // pageable source: staged before the call returns
-		if (ce != cudaSuccess) return ce;
-	}
-
 	// Bands: enough CTAs for ~16 waves of 4 CTAs/SM when the batch is small, tall strips (little
 	// vertical halo) when it is large; multiples of 8 rows; small enough that one band's vertical
 	// tables fit a launch's parameter block.
@@ -307,6 +354,20 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// the upscaling kernel is instantiated for windows of 3, 4 and 6 rows: slots are r % that
 	const int updepth = depth <= 3 ? 3 : depth <= 4 ? 4 : 6;
 	t.depth = use_up ? updepth : depth;
+
+	// The kernels fetch the descriptor from global memory, not from their parameter block (DESIGN 9): a slot
+	// of a per-device ring, written in stream order ahead of the launches (the upscaling kernel copies rows
+	// without a descriptor).
+	unsigned slot_index = 0;
+	CUtensorMap *dmap = nullptr;
+	if (!use_up) {
+		dmap = map_slot(&slot_index);
+		if (!dmap) return cudaErrorMemoryAllocation;
+		write_descriptor_kernel<<<1, 32, 0, stream>>>(dmap, map);
+		cudaError_t ce = cudaGetLastError();
+		if (ce != cudaSuccess) return ce;
+		*launches += 1;
+	}
 
 	FastLaunch a{};
 	a.map = dmap; a.dst = &dst; a.t = &t; a.n = n; a.channels = channels; a.smem_bytes = smem_total; a.stream = stream;
@@ -407,7 +468,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		g_last_resize_kernel = use_up ? 5 : use_down ? (dl.da.rq > 0 ? 6 : dl.group == 8 ? 4 : 3) : 2;
 		yb = ye;
 	}
-	return cudaSuccess;
+	return use_up ? cudaSuccess : map_slot_release(slot_index, stream);
 }
 
 }  // namespace picha_b200

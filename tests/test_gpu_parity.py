@@ -379,8 +379,11 @@ def test_resize_ill_conditioned_filters_take_the_exact_kernel(gpu):
         assert_resize_close(got, oracle_resize(img, dw, dh, filt, fw), True, (pixel, sw, sh, dw, dh, filt, fw))
     # the same filters at their usual widths are well conditioned and keep the throughput kernels
     img = rand_image(rng, 588, 1301, "r16g16b16a16")
-    P.resizeSync(img, {"width": 187, "height": 2849, "filter": "catmulrom"})
+    P.resizeSync(img, {"width": 187, "height": 420, "filter": "catmulrom"})
     assert P.last_resize_kernel() != 1
+    # (a vertical upscale with a horizontal downscale has no throughput kernel of its own: bit-exact kernel)
+    P.resizeSync(img, {"width": 187, "height": 2849, "filter": "catmulrom"})
+    assert P.last_resize_kernel() == 1
 
 
 def axis_matrix(filt, fw, src, dst, vertical):
@@ -520,6 +523,63 @@ def test_batch_matches_single_calls(gpu):
     cb = P.colorConvertBatchSync(imgs, {"pixel": "grey"}, device=-1)
     assert all(a.equalPixels(b) for a, b in zip(cs, cb))
     assert P.resizeBatchSync([], {"width": 4, "height": 4}) == []
+
+
+def test_batch_chunks_same_shape_runs_into_single_launches(gpu):
+    """The host batch path cuts runs of same-shape images into chunks of one launch each; shapes, strides and pinned /
+    pageable buffers may change from image to image.  Results equal the single calls; launches are far fewer than images."""
+    P = gpu
+    rng = np.random.default_rng(77)
+    shapes = [(300, 200, "rgba", 0)] * 11 + [(301, 200, "rgba", 0)] + [(300, 200, "rgba", 8)] * 14 + [(300, 200, "rgb", 0)] * 9 + \
+             [(640, 360, "rgb", 4)] * 5 + [(300, 200, "rgba", 0)] * 3
+    imgs = [rand_image(rng, w, h, px, pad=pad) for (w, h, px, pad) in shapes]
+    pins = []
+    try:
+        for i in (2, 3, 20, 30):          # a few sources in pinned memory, in the middle of runs
+            im = imgs[i]
+            ptr = N.lib.picha_b200_host_alloc(im.data.size)
+            assert ptr
+            pins.append(ptr)
+            buf = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_ubyte)), shape=(im.data.size,))
+            buf[:] = im.data
+            imgs[i] = Image({"width": im.width, "height": im.height, "pixel": im.pixel, "stride": im.stride, "data": buf})
+        opts = {"width": 75, "height": 50, "filter": "mitchel"}
+        singles = [P.resizeSync(im, opts) for im in imgs]
+        for device in (0, -1):
+            before = P.launch_count()
+            batch = P.resizeBatchSync(imgs, opts, device=device)
+            launches = P.launch_count() - before
+            assert all(a.equalPixels(b) for a, b in zip(singles, batch))
+            if device == 0:
+                assert launches <= 2 * 24, launches      # 43 images: at most 24 chunks (a descriptor write + a kernel each)
+        grey = [P.colorConvertSync(im, {"pixel": "greya"}) for im in imgs]
+        gb = P.colorConvertBatchSync(imgs, {"pixel": "greya"}, device=0)
+        assert all(a.equalPixels(b) for a, b in zip(grey, gb))
+    finally:
+        for ptr in pins:
+            N.lib.picha_b200_host_free(ptr)
+
+
+def test_first_calls_of_many_shapes_from_many_threads(gpu):
+    """Plans are built outside the device lock: 16 threads, 16 shapes nobody has asked for yet, all at once."""
+    P = gpu
+    rng = np.random.default_rng(78)
+    imgs = [rand_image(rng, 211 + 7 * i, 157 + 5 * i, "rgba") for i in range(16)]
+    got, errs = [None] * 16, []
+
+    def work(i):
+        try:
+            got[i] = P.resizeSync(imgs[i], {"width": 53 + i, "height": 41 + i, "filter": "catmulrom"})
+        except Exception as e:   # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(16)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    for i in range(16):
+        want = oracle_resize(imgs[i], 53 + i, 41 + i, "catmulrom", 1.0)
+        assert_resize_close(got[i], want, False, ("threads", i))
 
 
 def test_device_resident_batch_and_synthetic_parity(gpu):
