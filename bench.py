@@ -189,7 +189,8 @@ def time_device_steps(fn, steps, warmup):
     return per, evs[0].elapsed_time(evs[-1])
 
 
-def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_cpu=True, batch=None, extras=False):
+def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_cpu=True, batch=None, extras=False,
+                        with_latency=False):
     import numpy as np
     import torch
     import picha_b200 as P
@@ -258,6 +259,8 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
                 if rank == 0:
                     res["e2e_sharder"] = sharder_e2e(w, args, src, tag, fwidth, world)
                 barrier()
+    if with_latency and rank == 0 and world == 1 and "call_latency" not in res:
+        res["call_latency"] = [call_latency(w, src, tag, fwidth, t, calls=4) for t in (4, 16)]
     if with_cpu and rank == 0 and world == 1:
         res["cpu_baseline"] = cpu_baseline_resize(w, src, dst, args)
     del src, dst
@@ -398,27 +401,36 @@ def call_latency(w, src, tag, fwidth, threads, calls=8):
     from picha_b200 import _native as N
     host = HostImages(w, src, threads, pinned=False)
     lat, errs = [[] for _ in range(threads)], []
+    gate = threading.Barrier(threads + 1)
 
     def work(i):
         try:
-            for c in range(calls + 1):
+            for c in range(calls + 2):
+                if c == 2:
+                    gate.wait()          # every thread has its lane (stream, staging memory) and the plan: start the clock
                 t0 = time.perf_counter()
                 N.check(N.lib.picha_b200_resize(ctypes.byref(host.srcs[i]), ctypes.byref(host.dsts[i]), tag, fwidth))
-                if c:
+                if c >= 2:
                     lat[i].append(time.perf_counter() - t0)
         except Exception as e:   # pragma: no cover
             errs.append(repr(e))
+            gate.abort()
 
     ts = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
     [t.start() for t in ts]
+    try:
+        gate.wait()
+    except threading.BrokenBarrierError:
+        pass
+    t0 = time.perf_counter()
     [t.join() for t in ts]
     wall = time.perf_counter() - t0
     if errs:
         return {"error": errs[0]}
     flat = sorted(x for l in lat for x in l)
     return {"threads": threads, "median_ms": round(flat[len(flat) // 2] * 1e3, 3), "p90_ms": round(flat[int(len(flat) * 0.9)] * 1e3, 3),
-            "images_per_s": round(threads * (calls + 1) / wall, 1), "calls": len(flat)}
+            "images_per_s": round(threads * calls / wall, 1), "out_mpix_per_s": round(threads * calls * w["dw"] * w["dh"] / 1e6 / wall, 1),
+            "calls": len(flat), "buffers": "pageable"}
 
 
 def _cpu_pool_rate(fn, items, threads, passes=2):
@@ -704,7 +716,8 @@ def main():
 
     key = args.workload
     runner = run_resize_workload if key in RESIZE_WORKLOADS else run_convert_workload
-    res = runner(key, args, rank, world, local_rank, with_e2e=not args.no_e2e, with_cpu=not args.no_cpu)
+    kw = {"extras": not args.no_e2e} if key in RESIZE_WORKLOADS else {}
+    res = runner(key, args, rank, world, local_rank, with_e2e=not args.no_e2e, with_cpu=not args.no_cpu, **kw)
 
     also = {}
     extra = []
@@ -713,11 +726,16 @@ def main():
     elif args.also != "none":
         extra = [k for k in args.also.split(",") if k]
     for k in extra:
+        e2e_too = k == "cfg5" and not args.no_e2e        # the thumbnail pipeline is a host-buffer workload by definition
+        kw2 = {"with_latency": k == "cfg4" and not args.no_e2e} if k in RESIZE_WORKLOADS else {}
         r = (run_resize_workload if k in RESIZE_WORKLOADS else run_convert_workload)(
-            k, args, rank, world, local_rank, with_e2e=False, with_cpu=not args.no_cpu)
+            k, args, rank, world, local_rank, with_e2e=e2e_too, with_cpu=not args.no_cpu, **kw2)
         also[k] = {"value": round(r["value"], 1), "unit": "Mpix/s", "ms_per_step": round(r["ms_per_step"], 4),
                    "roofline_frac": r["roofline"]["frac"], "achieved_GBs": r["roofline"]["achieved"],
                    "images_per_gpu": r["images_per_gpu"], "cpu_baseline": r.get("cpu_baseline")}
+        for extra_key in ("e2e", "call_latency"):
+            if r.get(extra_key):
+                also[k][extra_key] = r[extra_key]
 
     if rank == 0 and world == 1 and args.also == "auto":
         also["cfg1"] = cfg1_latency(args)
@@ -733,6 +751,9 @@ def main():
             "e2e": res.get("e2e"), "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "roofline": res["roofline"], "cpu_baseline": res.get("cpu_baseline"),
         }
+        for extra_key in ("e2e_pageable", "call_latency", "e2e_sharder"):
+            if res.get(extra_key) is not None:
+                line[extra_key] = res[extra_key]
         if also:
             line["also"] = also
         print(json.dumps(line), flush=True)

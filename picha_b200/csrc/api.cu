@@ -610,27 +610,59 @@ int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *sr
 		if (!lanes[l]) { rc = PICHA_B200_ERR_CUDA; g_last_error = "cudaStreamCreate failed"; }
 	}
 	// chunk size: at least two chunks per lane when the batch allows (overlap), at most 32 images or ~128 MB of source
+	struct Chunk { int first, count; };
+	std::vector<Chunk> chunks;
 	const int by_count = n / (2 * kLanes) > 0 ? n / (2 * kLanes) : 1;
-	int chunk = 0;
-	for (int i = 0; i < n && !rc; ++chunk) {
+	for (int i = 0; i < n;) {
 		const size_t bytes = align_up(device_pitch(srcs[i]) * srcs[i].height, 256);
 		const int by_bytes = bytes > 0 && (size_t(128) << 20) / bytes > 0 ? (int)((size_t(128) << 20) / bytes) : 1;
 		const int kmax = by_count < by_bytes ? (by_count < 32 ? by_count : 32) : (by_bytes < 32 ? by_bytes : 32);
 		int k = 1;
 		while (i + k < n && k < kmax && same_shape(srcs[i], srcs[i + k]) && same_shape(dsts[i], dsts[i + k])) ++k;
-		const int l = chunk % kLanes;
-		if (busy[l]) { rc = finish(lanes[l]); busy[l] = false; if (rc) break; }
-		rc = submit_chunk(dev, lanes[l], op, k, srcs + i, dsts + i);
-		busy[l] = (rc == 0);
+		chunks.push_back(Chunk{i, k});
 		i += k;
 	}
-	for (int l = 0; l < kLanes; ++l) {
-		if (!lanes[l]) continue;
-		if (busy[l]) { int r2 = finish(lanes[l]); if (!rc) rc = r2; }
-		else if (rc) cudaStreamSynchronize(lanes[l]->stream);
+	// One host thread per lane takes chunks off a shared counter: re-pitching pageable images into pinned staging
+	// memory is a host memcpy (~10 GB/s per thread), and four of them keep the copy engine busy where one cannot.
+	std::atomic<int> next{0};
+	std::atomic<int> first_rc{rc};
+	std::string first_err;
+	std::mutex err_mu;
+	auto lane_loop = [&](int l, bool set_device) {
+		if (set_device && cudaSetDevice(ordinal) != cudaSuccess) { first_rc = PICHA_B200_ERR_CUDA; return; }
+		bool busy = false;
+		int my = 0;
+		while (!first_rc.load()) {
+			const int c = next.fetch_add(1);
+			if (c >= (int)chunks.size()) break;
+			if (busy) { my = finish(lanes[l]); busy = false; if (my) break; }
+			my = submit_chunk(dev, lanes[l], op, chunks[c].count, srcs + chunks[c].first, dsts + chunks[c].first);
+			if (my) break;
+			busy = true;
+		}
+		if (busy) { int r2 = finish(lanes[l]); if (!my) my = r2; }
+		else if (my || first_rc.load()) cudaStreamSynchronize(lanes[l]->stream);
 		lanes[l]->pending.clear();
-		dev->release(lanes[l]);
+		if (my) {
+			std::lock_guard<std::mutex> g(err_mu);
+			if (!first_rc.load()) { first_rc = my; first_err = g_last_error; }
+		}
+	};
+	if (!rc) {
+		const int workers = (int)chunks.size() < kLanes ? (int)chunks.size() : kLanes;
+		if (workers <= 1) {
+			lane_loop(0, false);
+		} else {
+			std::vector<std::thread> threads;
+			for (int l = 1; l < workers; ++l) threads.emplace_back(lane_loop, l, true);
+			lane_loop(0, false);
+			for (auto &t : threads) t.join();
+		}
+		rc = first_rc.load();
+		if (rc && !first_err.empty()) g_last_error = first_err;
 	}
+	for (int l = 0; l < kLanes; ++l)
+		if (lanes[l]) dev->release(lanes[l]);
 	return rc;
 }
 

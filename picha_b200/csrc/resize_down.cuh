@@ -886,7 +886,7 @@ struct DownLaunch {
 // launch never completes before its predecessor and whatever follows in the stream sees all of them.
 template <int DEPTH, bool DEEP, int C, int GR, int P2> cudaError_t launch_group(const DownLaunch &a) {
 	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.smem_bytes);
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (see resize_exact.cu)
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);

@@ -379,7 +379,7 @@ struct UpLaunch {
 template <int DEPTH, bool DEEP, int WPX, int C> cudaError_t launch_one(const UpLaunch &a) {
 	auto kern = resize_up_kernel<DEPTH, DEEP, WPX, C>;
 	const int smem_total = smem_bytes(a.ua.win_bytes);
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (see resize_exact.cu)
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((a.dst->width + TILE - 1) / TILE, a.bands, a.n);
