@@ -172,6 +172,22 @@ int picha_b200_color_convert_device(int n, const picha_b200_image *src0, int64_t
                                     float r_factor, float g_factor, float b_factor, void *stream);
 int picha_b200_cmyk_to_rgb_device(int n, const picha_b200_image *cmyk0, int64_t cmyk_step,
                                   const picha_b200_image *rgb0, int64_t rgb_step, void *stream);
+
+/* ---- resize, then convert, in one kernel ---------------------------------
+ * dst = doColorConvert(resizeImage(src)) -- src/resize.cc:270-280 followed by src/colorconvert.cc:171-188, the
+ * pair a thumbnailer runs back to back (index.js:62-72, README.md:33-37) -- without the intermediate image: the
+ * resize kernels put every resized pixel through the reference's conversion in their pack stage.  `dst` has the
+ * destination's size AND pixel format; r/g/b are resolved luma weights (picha_b200_resolve_color_settings).
+ * Results are those of the two calls in sequence (bit-identical with PICHA_B200_EXACT). */
+int picha_b200_resize_convert(const picha_b200_image *src, picha_b200_image *dst, int filter_tag, float filter_width,
+                              float r_factor, float g_factor, float b_factor, unsigned flags);
+int picha_b200_resize_convert_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, int filter_tag,
+                                    float filter_width, float r_factor, float g_factor, float b_factor,
+                                    unsigned flags, int device);
+int picha_b200_resize_convert_device(int n, const picha_b200_image *src0, int64_t src_step,
+                                     const picha_b200_image *dst0, int64_t dst_step, int filter_tag,
+                                     float filter_width, float r_factor, float g_factor, float b_factor,
+                                     unsigned flags, void *stream);
 /* Synthetic pixels, i.i.d. uniform over the full channel range, from a counter-based hash of
  * (seed, image, byte offset in the payload): the same bytes picha_b200.synthetic.fill_host
  * produces, so host and device can regenerate any image of a benchmark batch. */

@@ -8,7 +8,7 @@ benchmark uses.  Importing it requires the built library; there is no CPU fallba
 """
 from ._native import EXACT, FORCE_FAST, FILTERS, PIXELS, PichaError, lib   # noqa: F401
 from .api import (cmykToRgbSync, colorConvert, colorConvertBatchSync, colorConvertSync, resize,   # noqa: F401
-                  resizeBatchSync, resizeSync)
+                  resizeBatchSync, resizeConvertSync, resizeSync)
 from .image import Image   # noqa: F401
 
 

@@ -70,6 +70,13 @@ SIGNATURES = {
     "picha_b200_cmyk_to_rgb_device": (ctypes.c_int, [ctypes.c_int, _IMG_P, ctypes.c_int64, _IMG_P, ctypes.c_int64, ctypes.c_void_p]),
     "picha_b200_color_convert_batch": (ctypes.c_int, [ctypes.c_int, _IMG_P, _IMG_P, ctypes.c_float, ctypes.c_float,
                                                       ctypes.c_float, ctypes.c_int]),
+    "picha_b200_resize_convert": (ctypes.c_int, [_IMG_P, _IMG_P, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                 ctypes.c_float, ctypes.c_uint]),
+    "picha_b200_resize_convert_batch": (ctypes.c_int, [ctypes.c_int, _IMG_P, _IMG_P, ctypes.c_int, ctypes.c_float, ctypes.c_float,
+                                                       ctypes.c_float, ctypes.c_float, ctypes.c_uint, ctypes.c_int]),
+    "picha_b200_resize_convert_device": (ctypes.c_int, [ctypes.c_int, _IMG_P, ctypes.c_int64, _IMG_P, ctypes.c_int64, ctypes.c_int,
+                                                        ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                                        ctypes.c_uint, ctypes.c_void_p]),
     "picha_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "picha_b200_host_free": (None, [ctypes.c_void_p]),
     "picha_b200_resize_device": (ctypes.c_int, [ctypes.c_int, _IMG_P, ctypes.c_int64, _IMG_P, ctypes.c_int64,

@@ -170,6 +170,22 @@ def colorConvertSync(img, opts):
     return out
 
 
+def resizeConvertSync(img, opts):
+    """colorConvertSync(resizeSync(img, opts), opts) in one kernel (include/picha_b200.h: picha_b200_resize_convert):
+    `opts` carries resize's keys (width, height, filter, filterScale) and colorConvert's (pixel, redWeight, ...).
+    Not part of picha's JS surface; the fused form of the pair a thumbnailer calls back to back."""
+    if not _is_object(img) or not _is_object(opts):
+        raise TypeError("expected: resizeConvertSync(image, opts)")
+    src, keep, _, _, tag, fwidth, flags = _prepare_resize(img, opts)
+    to = PIXEL_ENUM.get(_get(opts, "pixel")) if isinstance(_get(opts, "pixel"), str) else None
+    if to is None:
+        raise N.PichaError(N.ERR_INVALID_PIXEL)
+    out, dst = _new_image(_to_uint32_as_int(_get(opts, "width")), _to_uint32_as_int(_get(opts, "height")), to)
+    r, g, b = _color_settings(opts)
+    N.check(N.lib.picha_b200_resize_convert(ctypes.byref(src), ctypes.byref(dst), tag, fwidth, r, g, b, flags))
+    return out
+
+
 def cmykToRgbSync(img):
     """The JPEG decoder's cmyk_to_rgb (src/jpegcodec.cc:36-42) on a whole image: `img` carries C, M, Y, K in
     an 'rgba' image; the result is 'rgb'.  Not part of picha's JS surface (the reference runs this loop

@@ -400,6 +400,18 @@ int check_resize(const picha_b200_image *s, const picha_b200_image *d, int tag, 
 	return 0;
 }
 
+// resize, then convert: the checks of both reference entry points, minus the equal-format requirement
+int check_resize_convert(const picha_b200_image *s, const picha_b200_image *d, int tag, float width) {
+	int rc = check_image(s);
+	if (rc) return rc;
+	if (s->width <= 0) return PICHA_B200_ERR_INVALID_IMAGE;
+	if (!d || d->width <= 0 || d->height <= 0) return PICHA_B200_ERR_INVALID_DIMENSIONS;
+	if (tag < 0 || tag >= PICHA_B200_NUM_FILTERS) return PICHA_B200_ERR_INVALID_FILTER;
+	if (width != width || width <= 0) return PICHA_B200_ERR_INVALID_FILTER_WIDTH;
+	if (pixel_info(d->pixel).bytes == 0) return PICHA_B200_ERR_INVALID_PIXEL;
+	return check_image(d);
+}
+
 int check_convert(const picha_b200_image *s, const picha_b200_image *d) {
 	int rc = check_image(s);
 	if (rc) return rc;
@@ -481,8 +493,11 @@ DevBatch dev_batch(uint8_t *base, int64_t step, size_t pitch, const picha_b200_i
 	return b;
 }
 
+// luma: resize, then convert to d.pixel in the kernels' pack stage (nullptr, or same format: plain resize)
 int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag, float width, unsigned flags,
-               cudaStream_t stream) {
+               cudaStream_t stream, const float *luma = nullptr) {
+	FuseArgs fuse{-1, 0.0f, 0.0f, 0.0f};
+	if (luma && d.pixel != s.pixel) fuse = FuseArgs{d.pixel, luma[0], luma[1], luma[2]};
 	std::shared_ptr<Plan> plan;
 	int rc = get_plan(dev, tag, width, s.width, s.height, d.width, d.height, &plan);
 	if (rc) return rc;
@@ -491,17 +506,17 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	// Small images are launch-latency bound either way, so they get the bit-exact kernel; the
 	// throughput kernel (within +-1 LSB) takes everything large enough for bandwidth to matter.
 	const bool large = (long long)s.width * s.height >= 128 * 128 &&
-	                   (long long)d.width * d.height * pixel_info(d.pixel).channels >= 4096;
+	                   (long long)d.width * d.height * pixel_info(s.pixel).channels >= 4096;
 	if (!(flags & PICHA_B200_EXACT) && (large || (flags & PICHA_B200_FORCE_FAST)) && plan->fast_tile_w[s.pixel] > 0) {
 		FastTables ft = plan->ft;
 		ft.tile_w = plan->fast_tile_w[s.pixel];
 		ft.align_px = plan->fast_align_px[s.pixel];
-		e = launch_resize_fast(s, d, n, ft, plan->fy, stream, &launches);
+		e = launch_resize_fast(s, d, n, ft, plan->fy, fuse, stream, &launches);
 		if (e == cudaErrorNotSupported) cudaGetLastError();
 	}
 	if (e == cudaErrorNotSupported) {
 		launches = 0;
-		e = launch_resize_exact(s, d, n, plan->t, stream, &launches);
+		e = launch_resize_exact(s, d, n, plan->t, fuse, stream, &launches);
 		g_last_resize_kernel = 1;
 	}
 	g_launches += launches;
@@ -531,6 +546,7 @@ struct Op {
 	int tag; float width; unsigned flags;   // resize
 	float r, g, b;                          // convert
 	bool cmyk;                              // convert: the JPEG decoder's cmyk_to_rgb instead of doColorConvert
+	bool fused;                             // resize, then convert to the destination's format (r, g, b as for convert)
 };
 
 bool same_shape(const picha_b200_image &a, const picha_b200_image &b) {
@@ -571,7 +587,8 @@ int submit_chunk(Device *dev, Lane *lane, const Op &op, int k, const picha_b200_
 	}
 	if ((rc = flush(k))) return rc;
 	DevBatch sb = dev_batch(lane->din.p, (int64_t)sstep, sp, s), db = dev_batch(lane->dout.p, (int64_t)dstep, dp, d);
-	rc = op.resize ? run_resize(dev, sb, db, k, op.tag, op.width, op.flags, lane->stream)
+	const float luma[3] = {op.r, op.g, op.b};
+	rc = op.resize ? run_resize(dev, sb, db, k, op.tag, op.width, op.flags, lane->stream, op.fused ? luma : nullptr)
 	               : run_convert(sb, db, k, op.r, op.g, op.b, lane->stream, op.cmyk);
 	if (rc) return rc;
 	run_begin = -1;
@@ -669,7 +686,8 @@ int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *sr
 int run_batch(const Op &op, int n, const picha_b200_image *srcs, picha_b200_image *dsts, int device) {
 	if (n < 0 || (n > 0 && (!srcs || !dsts))) return PICHA_B200_ERR_INVALID_ARGUMENT;
 	for (int i = 0; i < n; ++i) {
-		int rc = op.resize ? check_resize(&srcs[i], &dsts[i], op.tag, op.width) : check_convert(&srcs[i], &dsts[i]);
+		int rc = op.fused ? check_resize_convert(&srcs[i], &dsts[i], op.tag, op.width)
+		                  : op.resize ? check_resize(&srcs[i], &dsts[i], op.tag, op.width) : check_convert(&srcs[i], &dsts[i]);
 		if (rc) return rc;
 	}
 	const int ndev = device_count();
@@ -863,6 +881,40 @@ int picha_b200_color_convert_batch(int n, const picha_b200_image *srcs, picha_b2
 	Op op{};
 	op.resize = false; op.r = r; op.g = g; op.b = b;
 	return run_batch(op, n, srcs, dsts, device);
+}
+
+int picha_b200_resize_convert(const picha_b200_image *src, picha_b200_image *dst, int filter_tag, float filter_width,
+                              float r, float g, float b, unsigned flags) {
+	Range nvtx_range("picha_b200_resize_convert");
+	Op op{};
+	op.resize = true; op.fused = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags; op.r = r; op.g = g; op.b = b;
+	if (!src || !dst) return PICHA_B200_ERR_INVALID_IMAGE;
+	return run_batch(op, 1, src, dst, default_ordinal());
+}
+
+int picha_b200_resize_convert_batch(int n, const picha_b200_image *srcs, picha_b200_image *dsts, int filter_tag,
+                                    float filter_width, float r, float g, float b, unsigned flags, int device) {
+	Range nvtx_range("picha_b200_resize_convert_batch");
+	Op op{};
+	op.resize = true; op.fused = true; op.tag = filter_tag; op.width = filter_width; op.flags = flags; op.r = r; op.g = g; op.b = b;
+	return run_batch(op, n, srcs, dsts, device);
+}
+
+int picha_b200_resize_convert_device(int n, const picha_b200_image *src0, int64_t src_step, const picha_b200_image *dst0,
+                                     int64_t dst_step, int filter_tag, float filter_width, float r, float g, float b,
+                                     unsigned flags, void *stream) {
+	Range nvtx_range("picha_b200_resize_convert_device");
+	if (n < 0) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	int rc = check_resize_convert(src0, dst0, filter_tag, filter_width);
+	if (rc) return rc;
+	Device *dev = nullptr;
+	rc = current_device_checked(&dev);
+	if (rc) return rc;
+	if (n == 0) return 0;
+	DevBatch s = dev_batch(static_cast<uint8_t *>(src0->data), src_step, src0->stride, *src0);
+	DevBatch d = dev_batch(static_cast<uint8_t *>(dst0->data), dst_step, dst0->stride, *dst0);
+	const float luma[3] = {r, g, b};
+	return run_resize(dev, s, d, n, filter_tag, filter_width, flags, static_cast<cudaStream_t>(stream), luma);
 }
 
 void *picha_b200_host_alloc(size_t bytes) {

@@ -18,60 +18,11 @@
 //   convert_pixels_kernel -- any alignment / stride / width (subView inputs, row tails).
 #include "kernels.h"
 #include "pixel.cuh"
+#include "pixel_convert.cuh"
 
 namespace picha_b200 {
 
 namespace {
-
-template <bool SDEEP, bool DDEEP> __device__ __forceinline__ unsigned depth_convert(unsigned v) {
-	if (SDEEP == DDEEP) return v;
-	if (DDEEP) return v * 257u;
-	return (v * 255u + 32767u) / 65535u;
-}
-
-// One pixel, on integer channel values. SC/DC: channel counts. src/colorconvert.cc:24-134.
-// MAGIC: the luma inputs in[0..2] arrive as 0x4B000000 | v (the float 2^23 + v) straight out of a byte
-// permute, instead of as integers -- one instruction less per channel on the bandwidth path.
-// CMYK (4 x u8 -> 3 x u8 only): the JPEG decoder's cmyk_to_rgb, src/jpegcodec.cc:36-42 -- integer
-// c * k / 255 per channel, truncating.
-template <int SC, bool SDEEP, int DC, bool DDEEP, bool MAGIC = false, bool CMYK = false>
-__device__ __forceinline__ void convert_pixel(const unsigned *in, unsigned *out, float rf, float gf, float bf) {
-	constexpr unsigned ONE = DDEEP ? 65535u : 255u;
-	if constexpr (CMYK) {
-#pragma unroll
-		for (int c = 0; c < 3; ++c) out[c] = (in[c] * in[3]) / 255u;
-		return;
-	}
-	if constexpr (SC >= 3 && DC <= 2) {          // 3->1, 3->2, 4->1, 4->2: luma (alpha ignored or passed through)
-		float r = MAGIC ? unpack_magic<SDEEP>(in[0]) : unpack_value<SDEEP>(in[0]);
-		float g = MAGIC ? unpack_magic<SDEEP>(in[1]) : unpack_value<SDEEP>(in[1]);
-		float b = MAGIC ? unpack_magic<SDEEP>(in[2]) : unpack_value<SDEEP>(in[2]);
-		float l = __fadd_rn(__fadd_rn(__fmul_rn(r, rf), __fmul_rn(g, gf)), __fmul_rn(b, bf));
-		out[0] = pack_value<DDEEP>(l);
-		if constexpr (DC == 2) out[1] = (SC == 4) ? depth_convert<SDEEP, DDEEP>(in[3]) : ONE;
-	} else {
-	unsigned v[4];
-#pragma unroll
-	for (int c = 0; c < SC; ++c) v[c] = depth_convert<SDEEP, DDEEP>(in[c]);
-	if constexpr (SC == DC) {
-#pragma unroll
-		for (int c = 0; c < DC; ++c) out[c] = v[c];
-	} else if constexpr (SC == 1) {              // 1->2 (g,1)  1->3 (g,g,g)  1->4 (g,g,g,1)
-		out[0] = v[0];
-		if constexpr (DC == 2) out[1] = ONE;
-		if constexpr (DC >= 3) { out[1] = v[0]; out[2] = v[0]; }
-		if constexpr (DC == 4) out[3] = ONE;
-	} else if constexpr (SC == 2) {              // 2->1 g   2->3 (g,a,0)   2->4 (g,g,g,a)
-		out[0] = v[0];
-		if constexpr (DC == 3) { out[1] = v[1]; out[2] = 0u; }
-		if constexpr (DC == 4) { out[1] = v[0]; out[2] = v[0]; out[3] = v[1]; }
-	} else if constexpr (SC == 3) {              // 3->4 (r,g,b,1)
-		out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; out[3] = ONE;
-	} else {                           // 4->3 (r,g,b)
-		out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
-	}
-	}
-}
 
 constexpr int kWarps = 8;
 constexpr int kGroup = 128;   // pixels per warp step: 4 per lane

@@ -29,10 +29,18 @@ struct ResizeTables {
 	int max_band_rows;  // max over bands of band_rows
 };
 
+// "Resize, then convert" in one kernel (picha_b200_resize_convert): when dst_pixel >= 0 the resize kernels put every
+// resized pixel through the reference's format conversion in their pack stage (pixel_convert.cuh) and store it in
+// the destination's format; DevBatch::pixel of the destination is then that format.
+struct FuseArgs {
+	int dst_pixel;      // PixelMode of the destination, or -1: no conversion (destination format = source format)
+	float r, g, b;      // normalised luma weights (ColorSettings)
+};
+
 // Bit-exact separable resize (reference summation order, separate mul/add). Any format,
 // ratio, stride or alignment. Returns cudaErrorInvalidValue if the band does not fit in smem.
 cudaError_t launch_resize_exact(const DevBatch &src, const DevBatch &dst, int n,
-                                const ResizeTables &t, cudaStream_t stream, int *launches);
+                                const ResizeTables &t, const FuseArgs &fuse, cudaStream_t stream, int *launches);
 
 // Pixel-format conversion, bit-exact (integer identities for everything but luma, which is
 // float without contraction). Any stride or alignment.
@@ -85,7 +93,7 @@ struct FastAxisY;
 // uses the exact kernel). One launch per group of row bands whose vertical tables fit the
 // parameter block.
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &t,
-                               const FastAxisY &fy, cudaStream_t stream, int *launches);
+                               const FastAxisY &fy, const FuseArgs &fuse, cudaStream_t stream, int *launches);
 // Frees the TMA descriptor ring launch_resize_fast keeps on `device` (current and idle); the next call makes a new one.
 void release_resize_descriptors(int device);
 

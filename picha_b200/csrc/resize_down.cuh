@@ -25,6 +25,7 @@
 #ifndef PICHA_B200_RESIZE_DOWN_CUH
 #define PICHA_B200_RESIZE_DOWN_CUH
 
+#include "pixel_convert.cuh"
 #include "resize_fast.cuh"
 
 namespace picha_b200 {
@@ -147,6 +148,7 @@ struct DownArgs {
 	int rq, dx;     // source pixels per output pixel; taps per output <= rq * dx
 	int off0;       // nominal first tap of column x is rq * x + off0
 	int nl, br0;    // blocks of 4 columns below nl and from br0 on are irregular (image edges): own weight tables
+	FuseArgs fuse;  // resize, then convert: the pack stage stores the destination's pixel format
 };
 
 __device__ __forceinline__ void mbar_init_a(uint32_t bar, int count) {
@@ -254,6 +256,7 @@ struct Pass2Args {
 	int tmp, xw, xf, outt;
 	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
 	int xs2, out_stride, dstride, tw, ng, tid, direct, nb;
+	FuseArgs fuse;
 };
 
 // shared-memory output tile -> global memory, 16 bytes per thread where the destination allows it
@@ -416,8 +419,10 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 				uint32_t pv[C];
 #pragma unroll
 				for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
-				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * BPP;
-				if (BPP == 4 && !DEEP) {
+				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * (a.fuse.dst_pixel < 0 ? BPP : pixel_bytes(a.fuse.dst_pixel));
+				if (a.fuse.dst_pixel >= 0) {
+					convert_store<C, DEEP>(gp, pv, a.fuse);
+				} else if (BPP == 4 && !DEEP) {
 					const uint32_t lo = __byte_perm(pv[0], pv[1 % C], 0x0040), hi = __byte_perm(pv[2 % C], pv[3 % C], 0x0040);
 					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(lo, hi, 0x5410);
 				} else if (BPP == 4) {
@@ -452,6 +457,7 @@ struct Pass2IntArgs {
 	int blk0;            // the tile's first block in the image (x0 / 4)
 	int nl, br0;         // DownArgs
 	int vec;             // destination rows are 16-byte aligned: a block leaves as 16-byte stores
+	FuseArgs fuse;
 };
 
 // RQ source pixels per output pixel, at most RQ * DX taps per output.  Lanes: 8 neighbouring blocks x 4 rows.
@@ -494,6 +500,11 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 			uint32_t pv[4];
 #pragma unroll
 			for (int ch = 0; ch < 4; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
+			if (a.fuse.dst_pixel >= 0) {     // resize, then convert: stored here, in the destination's format
+				if (U * i + u < a.tw)
+					convert_store<4, DEEP>(a.gbase + (long long)g * a.dstride + (long long)(U * i + u) * pixel_bytes(a.fuse.dst_pixel), pv, a.fuse);
+				continue;
+			}
 			if (DEEP) {
 				px[u][0] = __byte_perm(pv[0], pv[1], 0x5410);
 				px[u][DEEP ? 1 : 0] = __byte_perm(pv[2], pv[3], 0x5410);
@@ -501,6 +512,7 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 				px[u][0] = __byte_perm(__byte_perm(pv[0], pv[1], 0x0040), __byte_perm(pv[2], pv[3], 0x0040), 0x5410);
 			}
 		}
+		if (a.fuse.dst_pixel >= 0) continue;
 		uint8_t *gp = a.gbase + (long long)g * a.dstride + (long long)(U * i) * BPP;
 		if (a.vec && U * i + U <= a.tw) {
 			if (DEEP) {
@@ -724,7 +736,8 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	Pass2Args pa;
 	pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
 	pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
-	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * BPP;
+	pa.fuse = da.fuse;
+	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * (da.fuse.dst_pixel < 0 ? BPP : pixel_bytes(da.fuse.dst_pixel));
 	const uint32_t my_tmp = sbase + L.tmp + tid * 16;
 	// integer-ratio pass: where this thread's four units of an intermediate row go (one unit of padding after every
 	// 4 * rq units, counted from c0)
@@ -740,6 +753,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
 		pi.c0 = c0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
 		pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
+		pi.fuse = da.fuse;
 	}
 
 	// The row loop.  Which rows complete an output is not computed here: the host has put the number of outputs

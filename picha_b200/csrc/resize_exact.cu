@@ -10,6 +10,7 @@
 // the per-tap effective rows (tables.cc).
 #include "kernels.h"
 #include "pixel.cuh"
+#include "pixel_convert.cuh"
 
 namespace picha_b200 {
 
@@ -19,7 +20,7 @@ constexpr int kThreads = 256;
 
 template <int CH, bool DEEP>
 __global__ void __launch_bounds__(kThreads)
-resize_exact_kernel(DevBatch src, DevBatch dst, ResizeTables t) {
+resize_exact_kernel(DevBatch src, DevBatch dst, ResizeTables t, FuseArgs fuse) {
 	extern __shared__ float tmp[];   // [band rows][tw][CH]
 	constexpr int BPP = CH * Depth<DEEP>::bytes;
 
@@ -66,14 +67,22 @@ resize_exact_kernel(DevBatch src, DevBatch dst, ResizeTables t) {
 #pragma unroll
 			for (int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(wk, v[c]));
 		}
-		uint8_t *d = dimg + (int64_t)y * dst.stride + (int64_t)(x0 + xx) * BPP;
+		if (fuse.dst_pixel < 0) {
+			uint8_t *d = dimg + (int64_t)y * dst.stride + (int64_t)(x0 + xx) * BPP;
 #pragma unroll
-		for (int c = 0; c < CH; ++c) store_channel<DEEP>(d + c * Depth<DEEP>::bytes, pack_value<DEEP>(acc[c]));
+			for (int c = 0; c < CH; ++c) store_channel<DEEP>(d + c * Depth<DEEP>::bytes, pack_value<DEEP>(acc[c]));
+		} else {
+			// resize, then convert (src/colorconvert.cc:136-152 on the pixel src/resize.cc:128-131 would have stored)
+			unsigned pv[CH];
+#pragma unroll
+			for (int c = 0; c < CH; ++c) pv[c] = pack_value<DEEP>(acc[c]);
+			convert_store<CH, DEEP>(dimg + (int64_t)y * dst.stride + (int64_t)(x0 + xx) * pixel_bytes(fuse.dst_pixel), pv, fuse);
+		}
 	}
 }
 
 template <int CH, bool DEEP>
-cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const ResizeTables &t, cudaStream_t stream) {
+cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const ResizeTables &t, const FuseArgs &fuse, cudaStream_t stream) {
 	const size_t smem = (size_t)t.max_band_rows * t.tile_w * CH * sizeof(float);
 	if (smem > (size_t)max_dynamic_smem()) return cudaErrorInvalidValue;
 	auto kern = resize_exact_kernel<CH, DEEP>;
@@ -86,7 +95,7 @@ cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const Resize
 		s.base += (int64_t)z0 * src.step;
 		d.base += (int64_t)z0 * dst.step;
 		dim3 grid((dst.width + t.tile_w - 1) / t.tile_w, bands, nz);
-		kern<<<grid, kThreads, smem, stream>>>(s, d, t);
+		kern<<<grid, kThreads, smem, stream>>>(s, d, t, fuse);
 	}
 	return cudaGetLastError();
 }
@@ -94,17 +103,17 @@ cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const Resize
 }  // namespace
 
 cudaError_t launch_resize_exact(const DevBatch &src, const DevBatch &dst, int n, const ResizeTables &t,
-                                cudaStream_t stream, int *launches) {
+                                const FuseArgs &fuse, cudaStream_t stream, int *launches) {
 	*launches += (n + 65534) / 65535;
 	switch (src.pixel) {
-		case 0: return launch<3, false>(src, dst, n, t, stream);
-		case 1: return launch<4, false>(src, dst, n, t, stream);
-		case 2: return launch<1, false>(src, dst, n, t, stream);
-		case 3: return launch<2, false>(src, dst, n, t, stream);
-		case 4: return launch<1, true>(src, dst, n, t, stream);
-		case 5: return launch<2, true>(src, dst, n, t, stream);
-		case 6: return launch<3, true>(src, dst, n, t, stream);
-		case 7: return launch<4, true>(src, dst, n, t, stream);
+		case 0: return launch<3, false>(src, dst, n, t, fuse, stream);
+		case 1: return launch<4, false>(src, dst, n, t, fuse, stream);
+		case 2: return launch<1, false>(src, dst, n, t, fuse, stream);
+		case 3: return launch<2, false>(src, dst, n, t, fuse, stream);
+		case 4: return launch<1, true>(src, dst, n, t, fuse, stream);
+		case 5: return launch<2, true>(src, dst, n, t, fuse, stream);
+		case 6: return launch<3, true>(src, dst, n, t, fuse, stream);
+		case 7: return launch<4, true>(src, dst, n, t, fuse, stream);
 	}
 	return cudaErrorInvalidValue;
 }

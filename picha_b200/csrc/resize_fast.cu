@@ -182,7 +182,7 @@ void release_resize_descriptors(int device) {
 }
 
 cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, const FastTables &tables,
-                               const FastAxisY &fy, cudaStream_t stream, int *launches) {
+                               const FastAxisY &fy, const FuseArgs &fuse, cudaStream_t stream, int *launches) {
 	static const int kBytes[8] = {3, 4, 1, 2, 2, 4, 6, 8}, kChannels[8] = {3, 4, 1, 2, 1, 2, 3, 4};
 	const int bpp = kBytes[src.pixel], channels = kChannels[src.pixel];
 	const bool deep = src.pixel >= 4;
@@ -211,12 +211,15 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		dl.da.xscale = std::ldexp(1.0f, 149 - down::kVExp) / (deep ? 65535.0f : 255.0f);
 		const int store_unit = (bpp == 4 || bpp == 8) ? bpp : (bpp == 2 && !deep) ? 2 : deep ? 2 : 1;
 		dl.da.direct = ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)dst.step) & (store_unit - 1)) == 0;
+		dl.da.fuse = fuse;
+		if (fuse.dst_pixel >= 0) dl.da.direct = 1;   // converted pixels are stored channel by channel: any alignment
 	}
 	// 4-channel upscales with a shallow row window take the kernel of resize_up.cuh.
 	// Upscales with a shallow row window take the kernel of resize_up.cuh (its stores are whole words
 	// up to 16 bytes: the destination must be 16-byte aligned, which the library's own layout is).
 	bool use_up = fy.variant == FastAxisY::kUp && depth <= up::kMaxDepth && !getenv("PICHA_B200_OLD_UP") &&
-	              ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)(n > 1 ? dst.step : 0)) & 15) == 0;
+	              (fuse.dst_pixel >= 0 ||
+	               ((reinterpret_cast<uintptr_t>(dst.base) | (uintptr_t)dst.stride | (uintptr_t)(n > 1 ? dst.step : 0)) & 15) == 0);
 	UpLaunch ul{};
 	const int *host_xfirst = t.h_xfirst, *host_xcount = t.h_xcount;
 	const float *host_xw = t.h_xw;
@@ -243,13 +246,14 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		ul.wpx = wpx;
 		ul.ua.win_bytes = (win_px * bpp + 15) & ~15;
 		ul.ua.hscale = std::ldexp(1.0f, up::kHExp);
+		ul.ua.fuse = fuse;
 		if (up::smem_bytes(ul.ua.win_bytes) > max_dynamic_smem()) use_up = false;
 	}
 	// The generic kernel is not a default route any more: shapes neither specialised kernel takes (vertical depth
 	// above 8; a vertical upscale with a horizontal downscale; misaligned destinations of upscales) get the bit-exact
 	// kernel.  It once failed with an illegal address under a fuzz sequence and the cause was never pinned down
 	// (DESIGN.md section 9); PICHA_B200_GENERIC=1 (and the A/B switch PICHA_B200_OLD_UP) still reach it.
-	if (!use_down && !use_up && !getenv("PICHA_B200_GENERIC") && !getenv("PICHA_B200_OLD_UP")) return cudaErrorNotSupported;
+	if (!use_down && !use_up && (fuse.dst_pixel >= 0 || (!getenv("PICHA_B200_GENERIC") && !getenv("PICHA_B200_OLD_UP")))) return cudaErrorNotSupported;
 	if (use_down) {
 		// Rows per pass-2 group.  With 4, the eight lanes that share a shared-memory phase of a float4 read
 		// are four rows of two neighbouring columns; they hit distinct banks only if the columns' windows

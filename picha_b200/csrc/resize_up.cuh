@@ -49,6 +49,7 @@ constexpr int kMaxDepth = 6;
 struct UpArgs {
 	int win_bytes;     // bytes of a source row staged per tile (multiple of 16)
 	float hscale;      // 2^kHExp
+	FuseArgs fuse;     // resize, then convert: the pack stage stores the destination's pixel format
 };
 
 __host__ __device__ inline int smem_bytes(int win_bytes) { return NS * RS * win_bytes + 2 * NS * 8; }
@@ -199,7 +200,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		--fleft;
 	};
 
-	uint8_t *const dcol = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * BPP;
+	uint8_t *const dcol = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * (ua.fuse.dst_pixel < 0 ? BPP : pixel_bytes(ua.fuse.dst_pixel));
 	const int npx = any ? min(NPX, dst.width - px0) : 0;
 
 	uint32_t raw[WPX * WPP];
@@ -323,7 +324,12 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 					q[i] = __byte_perm(lo, hi, 0x5410);
 				}
 			}
-			if (npx == NPX) {
+			if (ua.fuse.dst_pixel >= 0) {
+				// resize, then convert: each of the thread's pixels goes through the reference's conversion
+#pragma unroll
+				for (int p = 0; p < NPX; ++p)
+					if (p < npx) convert_store<C, DEEP>(drow + p * pixel_bytes(ua.fuse.dst_pixel), pv + C * p, ua.fuse);
+			} else if (npx == NPX) {
 				if (NW % 4 == 0) {
 #pragma unroll
 					for (int i = 0; i < NW / 4; ++i) reinterpret_cast<uint4 *>(drow)[i] = make_uint4(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);

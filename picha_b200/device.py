@@ -82,3 +82,22 @@ def color_convert(src, dst, weights=None):
         N.check(N.lib.picha_b200_color_convert_device(src.n, ctypes.byref(s), src.step, ctypes.byref(d), dst.step,
                                                       out[0], out[1], out[2],
                                                       torch.cuda.current_stream().cuda_stream))
+
+
+def resize_convert(src, dst, filter=None, filter_scale=None, weights=None, exact=False):
+    """dst[i] = doColorConvert(resizeImage(src[i])) in one kernel; dst has the target size AND pixel format."""
+    tag_out, width_out = ctypes.c_int(0), ctypes.c_float(0)
+    has_filter = filter is not None
+    N.check(N.lib.picha_b200_resolve_resize_options(int(has_filter), N.FILTERS.index(filter) if has_filter else 0,
+                                                    int(filter_scale is not None),
+                                                    float(filter_scale if filter_scale is not None else 0.0),
+                                                    ctypes.byref(tag_out), ctypes.byref(width_out)))
+    out = (ctypes.c_float * 3)()
+    nan = float("nan")
+    r, g, b = weights if weights is not None else (nan, nan, nan)
+    N.lib.picha_b200_resolve_color_settings(r, g, b, out)
+    s, d = src.cimage(), dst.cimage()
+    with torch.cuda.device(src.device):
+        N.check(N.lib.picha_b200_resize_convert_device(src.n, ctypes.byref(s), src.step, ctypes.byref(d), dst.step,
+                                                       tag_out.value, width_out.value, out[0], out[1], out[2],
+                                                       N.EXACT if exact else 0, torch.cuda.current_stream().cuda_stream))

@@ -525,6 +525,45 @@ def test_batch_matches_single_calls(gpu):
     assert P.resizeBatchSync([], {"width": 4, "height": 4}) == []
 
 
+def test_resize_convert_fused_equals_the_two_reference_calls(gpu):
+    """picha_b200_resize_convert = doColorConvert(resizeImage(src)) (src/colorconvert.cc:171-188 on the output of
+    src/resize.cc:270-280) in one kernel.  Exact mode: identical to the reference's two calls, every format pair.
+    Throughput kernels: identical to this library's own resize followed by its (bit-exact) conversion, and within
+    the resize tolerance of the reference pair where the conversion is monotone per channel."""
+    P = gpu
+    rng = np.random.default_rng(99)
+    launches = []
+    for sp in PIXEL_NAMES:
+        if sp == "r16b16":
+            continue
+        for dp in PIXEL_NAMES:
+            if dp == "r16b16":
+                continue
+            img = rand_image(rng, 61, 47, sp)
+            ref = oracle_resize(img, 33, 29, "cubic", 0.7)
+            want, ws = O.color_convert(np.ascontiguousarray(ref.data), ref.stride, 33, 29, sp, dp)
+            got = P.resizeConvertSync(img, {"width": 33, "height": 29, "pixel": dp, "exact": True})
+            assert np.array_equal(got.rows(), O.payload(want, ws, 33, 29, dp)), (sp, dp)
+    # throughput kernels: downscale (general and integer-ratio passes), upscale, 8- and 16-bit, custom luma weights
+    cases = [("rgba", "rgb", 1024, 600, 256, 150, "lanczos"), ("rgba", "grey", 1000, 333, 500, 111, "cubic"),
+             ("rgb", "greya", 1200, 640, 160, 160, None), ("r16g16b16a16", "rgb", 800, 1200, 237, 300, "lanczos"),
+             ("rgb", "r16g16b16a16", 900, 500, 300, 250, "triangle"), ("greya", "rgba", 1280, 720, 427, 241, "catmulrom"),
+             ("rgba", "greya", 300, 200, 1500, 1700, "mitchel"), ("r16g16b16a16", "grey", 257, 400, 771, 1601, "catmulrom"),
+             ("rgb", "rgba", 333, 222, 1001, 667, "mitchel"), ("grey", "rgb", 400, 300, 1203, 450, "catmulrom")]
+    for sp, dp, sw, sh, dw, dh, filt in cases:
+        img = rand_image(rng, sw, sh, sp)
+        opts = {"width": dw, "height": dh, "pixel": dp, "redWeight": 0.3, "greenWeight": 0.5, "blueWeight": 0.2}
+        if filt:
+            opts["filter"] = filt
+        before = P.launch_count()
+        got = P.resizeConvertSync(img, opts)
+        launches.append(P.launch_count() - before)
+        k = P.last_resize_kernel()
+        assert k in (3, 4, 5, 6), (sp, dp, k)
+        two = P.colorConvertSync(P.resizeSync(img, opts), opts)
+        assert got.equalPixels(two), (sp, dp, "fused differs from resize + convert", k)
+
+
 def test_batch_chunks_same_shape_runs_into_single_launches(gpu):
     """The host batch path cuts runs of same-shape images into chunks of one launch each; shapes, strides and pinned /
     pageable buffers may change from image to image.  Results equal the single calls; launches are far fewer than images."""
