@@ -42,6 +42,9 @@ RESIZE_WORKLOADS = {
     "cfg5": dict(sw=1920, sh=1080, dw=256, dh=256, pixel="rgb", filter=None, width=0.70, batch=1024, seed=1239,
                  name="cfg5: 1080p rgb -> 256x256 cubic@0.70 thumbnails, 1024 per GPU (8192 on 8)"),
 }
+# resize, then convert, in one kernel (picha_b200_resize_convert): the thumbnail pipeline straight to grey
+RESIZE_WORKLOADS["cfg5-grey"] = dict(RESIZE_WORKLOADS["cfg5"], to="grey", seed=1239,
+                                     name="cfg5 fused: 1080p rgb -> 256x256 cubic@0.70 -> grey in one kernel, 1024 per GPU")
 CONVERT_WORKLOADS = {
     "cfg2": dict(w=1920, h=1080, src="rgba", dst="rgb", batch=256, seed=1236,
                  name="cfg2: 1080p rgba -> rgb colorConvert, batch 256 per GPU"),
@@ -201,16 +204,23 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     n = batch or w["batch"]
     bpp = PIXEL_BYTES[w["pixel"]]
     src = D.DeviceBatch(n, w["sw"], w["sh"], w["pixel"])
-    dst = D.DeviceBatch(n, w["dw"], w["dh"], w["pixel"])
+    dst = D.DeviceBatch(n, w["dw"], w["dh"], w.get("to", w["pixel"]))
     src.fill_synthetic(w["seed"], first_image=rank * n)     # every rank owns its own block of images
     torch.cuda.synchronize()
     tag, fwidth = resolve_filter(P, w)
     s0, d0 = src.cimage(), dst.cimage()
     stream = torch.cuda.current_stream().cuda_stream
 
+    cs = (ctypes.c_float * 3)()
+    N.lib.picha_b200_resolve_color_settings(float("nan"), float("nan"), float("nan"), cs)
+
     def step():
-        N.check(N.lib.picha_b200_resize_device(n, ctypes.byref(s0), src.step, ctypes.byref(d0), dst.step, tag, fwidth,
-                                               0, stream))
+        if "to" in w:
+            N.check(N.lib.picha_b200_resize_convert_device(n, ctypes.byref(s0), src.step, ctypes.byref(d0), dst.step, tag, fwidth,
+                                                           cs[0], cs[1], cs[2], 0, stream))
+        else:
+            N.check(N.lib.picha_b200_resize_device(n, ctypes.byref(s0), src.step, ctypes.byref(d0), dst.step, tag, fwidth,
+                                                   0, stream))
 
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     launches0 = P.launch_count()
@@ -228,7 +238,7 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     total_mpix = sum_over_ranks(out_mpix_rank)
     value = total_mpix / (ms_per_step / 1e3)
 
-    algo_bytes = n * (w["sw"] * w["sh"] + w["dw"] * w["dh"]) * bpp      # payload read + written per step
+    algo_bytes = n * (w["sw"] * w["sh"] * bpp + w["dw"] * w["dh"] * PIXEL_BYTES[w.get("to", w["pixel"])])   # payload read + written per step
     launch_ms = sum(per) / len(per)                                       # the step's resize launches, back to back
     peak, peak_src = measured_peak()
     achieved = algo_bytes / (launch_ms / 1e3) / 1e9
@@ -242,6 +252,8 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
     res = {"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "gpu_launches": launches,
            "clocks": clocks, "images_per_gpu": n}
 
+    if "to" in w:
+        with_e2e = with_cpu = with_latency = False      # (device-resident line only; parity of the fused op is in tests/)
     if with_e2e:
         big = key == "cfg5"            # thumbnails: enough images per step for the library to cut chunks of one launch each
         res["e2e"] = e2e_resize(w, args, rank, local_rank, src, tag, fwidth, batch=min(256, n) if big else None)
@@ -722,7 +734,7 @@ def main():
     also = {}
     extra = []
     if args.also == "auto":
-        extra = [k for k in ("cfg2", "cfg2-grey", "cfg2-greya", "cfg4", "cfg5") if k != key] if world == 1 else []
+        extra = [k for k in ("cfg2", "cfg2-grey", "cfg2-greya", "cfg4", "cfg5", "cfg5-grey") if k != key] if world == 1 else []
     elif args.also != "none":
         extra = [k for k in args.also.split(",") if k]
     for k in extra:

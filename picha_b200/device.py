@@ -101,3 +101,137 @@ def resize_convert(src, dst, filter=None, filter_scale=None, weights=None, exact
         N.check(N.lib.picha_b200_resize_convert_device(src.n, ctypes.byref(s), src.step, ctypes.byref(d), dst.step,
                                                        tag_out.value, width_out.value, out[0], out[1], out[2],
                                                        N.EXACT if exact else 0, torch.cuda.current_stream().cuda_stream))
+
+
+class DeviceImage:
+    """picha's Image (lib/image.js) with its pixels resident in HBM: the same fields (data, width, height, pixel,
+    stride) and the same stride semantics, `data` being a 1-D torch uint8 CUDA tensor instead of a Buffer.
+    ``row`` / ``subView`` share the storage exactly like Buffer.slice does (lib/image.js:42-44,76-87), ``copy`` copies
+    the overlapping payload (:89-96) with one strided device copy; ``resize`` / ``colorConvert`` / ``resizeConvert`` call
+    the C-ABI's *_device entry points on torch's current stream -- a chain such as
+    ``img.resize(...).subView(...).colorConvert(...)`` never crosses PCIe.
+    """
+
+    def __init__(self, opt=None, **kw):
+        opt = dict(opt or {}, **kw)
+        self.width, self.height = opt.get("width") or 0, opt.get("height") or 0
+        self.pixel = opt.get("pixel") or "rgba"
+        psize = PIXEL_SIZES.get(self.pixel, 0)
+        if psize == 0:
+            raise ValueError("invalid pixel format " + str(self.pixel))
+        # default pitch: 128-byte rows (every row line-aligned and TMA-addressable); any stride >= width*bytes is accepted
+        self.stride = opt.get("stride") or _align(self.width * psize, 128)
+        if self.stride < self.width * psize:
+            raise ValueError("stride too short")
+        if self.width < 0 or self.height < 0:
+            raise ValueError("invalid dimensions")
+        self.data = opt.get("data")
+        if self.data is None:
+            dev = opt.get("device") or torch.device("cuda", torch.cuda.current_device())
+            self.data = torch.empty(max(self.stride * self.height, 1), dtype=torch.uint8, device=dev)
+        if self.data.dtype != torch.uint8 or self.data.dim() != 1 or not self.data.is_cuda:
+            raise ValueError("data must be a 1-D uint8 CUDA tensor")
+        if self.data.numel() < self.stride * (self.height - 1) + self.width * psize:
+            raise ValueError("image data too small")
+
+    # ---- lib/image.js semantics -----------------------------------------------------------------
+    def pixelSize(self):
+        return PIXEL_SIZES[self.pixel]
+
+    def row(self, y):
+        return self.data[y * self.stride:y * self.stride + self.width * self.pixelSize()]
+
+    def rows(self):
+        """(height, width*bytes) strided view of the payload (shares storage)."""
+        return torch.as_strided(self.data, (self.height, self.width * self.pixelSize()), (self.stride, 1))
+
+    def subView(self, x, y, w, h):
+        p = self.pixelSize()
+        off = y * self.stride + x * p
+        return DeviceImage({"width": w, "height": h, "pixel": self.pixel, "stride": self.stride,
+                            "data": self.data[off:off + (h - 1) * self.stride + w * p]})
+
+    def copy(self, target):
+        if target.pixel != self.pixel:
+            raise ValueError("can't copy pixels between different pixel types")
+        w, h = min(self.width, target.width), min(self.height, target.height)
+        if w and h:
+            rw = w * self.pixelSize()
+            torch.as_strided(target.data, (h, rw), (target.stride, 1)).copy_(torch.as_strided(self.data, (h, rw), (self.stride, 1)))
+
+    def equalPixels(self, o):
+        if self.width != o.width or self.height != o.height or self.pixel != o.pixel:
+            return False
+        return bool(torch.equal(self.rows(), o.rows()))
+
+    # ---- host <-> device ------------------------------------------------------------------------
+    @staticmethod
+    def from_host(image, device=None):
+        out = DeviceImage({"width": image.width, "height": image.height, "pixel": image.pixel, "device": device})
+        if image.width and image.height:
+            out.rows().copy_(torch.from_numpy(image.rows().copy()))
+        return out
+
+    def to_host(self):
+        out = Image({"width": self.width, "height": self.height, "pixel": self.pixel})
+        if self.width and self.height:
+            rw = self.width * self.pixelSize()
+            import numpy as np
+            np.lib.stride_tricks.as_strided(out.data, shape=(self.height, rw), strides=(out.stride, 1))[:] = self.rows().cpu().numpy()
+        return out
+
+    # ---- the hot path, on the device ----------------------------------------------------------------
+    def _cimage(self):
+        return N.CImage(self.data.data_ptr(), self.stride, self.width, self.height, PIXEL_ENUM[self.pixel])
+
+    def _resize_options(self, opts):
+        tag, width = ctypes.c_int(0), ctypes.c_float(0)
+        f, fs = opts.get("filter"), opts.get("filterScale")
+        if f is not None and f not in N.FILTERS:
+            raise N.PichaError(N.ERR_INVALID_FILTER)
+        N.check(N.lib.picha_b200_resolve_resize_options(int(f is not None), N.FILTERS.index(f) if f is not None else 0,
+                                                        int(fs is not None), float(fs if fs is not None else 0.0),
+                                                        ctypes.byref(tag), ctypes.byref(width)))
+        return tag.value, width.value
+
+    @staticmethod
+    def _luma(opts):
+        out = (ctypes.c_float * 3)()
+        nan = float("nan")
+        N.lib.picha_b200_resolve_color_settings(opts.get("redWeight", nan), opts.get("greenWeight", nan), opts.get("blueWeight", nan), out)
+        return out[0], out[1], out[2]
+
+    def resize(self, opts):
+        """picha.resizeSync(image, opts) (index.js:19-21) without leaving the device."""
+        tag, fwidth = self._resize_options(opts)
+        dst = DeviceImage({"width": int(opts["width"]), "height": int(opts["height"]), "pixel": self.pixel, "device": self.data.device})
+        s, d = self._cimage(), dst._cimage()
+        with torch.cuda.device(self.data.device):
+            N.check(N.lib.picha_b200_resize_device(1, ctypes.byref(s), 0, ctypes.byref(d), 0, tag, fwidth,
+                                                   N.EXACT if opts.get("exact") else 0, torch.cuda.current_stream().cuda_stream))
+        return dst
+
+    def colorConvert(self, opts):
+        """picha.colorConvertSync(image, opts) (index.js:31-33) without leaving the device."""
+        if opts.get("pixel") not in PIXEL_ENUM:
+            raise N.PichaError(N.ERR_INVALID_PIXEL)
+        dst = DeviceImage({"width": self.width, "height": self.height, "pixel": opts["pixel"], "device": self.data.device})
+        r, g, b = self._luma(opts)
+        s, d = self._cimage(), dst._cimage()
+        with torch.cuda.device(self.data.device):
+            N.check(N.lib.picha_b200_color_convert_device(1, ctypes.byref(s), 0, ctypes.byref(d), 0, r, g, b,
+                                                          torch.cuda.current_stream().cuda_stream))
+        return dst
+
+    def resizeConvert(self, opts):
+        """colorConvert(resize(image)) in one kernel (picha_b200_resize_convert_device)."""
+        if opts.get("pixel") not in PIXEL_ENUM:
+            raise N.PichaError(N.ERR_INVALID_PIXEL)
+        tag, fwidth = self._resize_options(opts)
+        dst = DeviceImage({"width": int(opts["width"]), "height": int(opts["height"]), "pixel": opts["pixel"], "device": self.data.device})
+        r, g, b = self._luma(opts)
+        s, d = self._cimage(), dst._cimage()
+        with torch.cuda.device(self.data.device):
+            N.check(N.lib.picha_b200_resize_convert_device(1, ctypes.byref(s), 0, ctypes.byref(d), 0, tag, fwidth, r, g, b,
+                                                           N.EXACT if opts.get("exact") else 0, torch.cuda.current_stream().cuda_stream))
+        return dst

@@ -564,6 +564,37 @@ def test_resize_convert_fused_equals_the_two_reference_calls(gpu):
         assert got.equalPixels(two), (sp, dp, "fused differs from resize + convert", k)
 
 
+def test_device_image_chain_never_leaves_the_device(gpu):
+    """DeviceImage = lib/image.js's Image on HBM-resident pixels: resize -> subView -> colorConvert, copy
+    and row on the device give what the reference chain gives on the host (README.md:33-37, test/copy.js:18-22)."""
+    import torch
+    from picha_b200.device import DeviceImage
+    P = gpu
+    rng = np.random.default_rng(123)
+    host = rand_image(rng, 640, 480, "rgba", pad=12)
+    dimg = DeviceImage.from_host(host)
+    assert dimg.to_host().equalPixels(host)
+    # the chain on the device, exact kernels, against the compiled reference on the host
+    small = dimg.resize({"width": 200, "height": 150, "filter": "lanczos", "exact": True})
+    view = small.subView(17, 9, 101, 77)                         # odd offsets: unaligned base, parent's stride
+    grey = view.colorConvert({"pixel": "greya"})
+    ref_small = oracle_resize(host, 200, 150, "lanczos", 1.0)
+    ref_view = ref_small.subView(17, 9, 101, 77)
+    want, ws = O.color_convert(np.ascontiguousarray(ref_view.data), ref_view.stride, 101, 77, "rgba", "greya")
+    assert np.array_equal(grey.to_host().rows(), O.payload(want, ws, 101, 77, "greya"))
+    assert view.to_host().equalPixels(ref_view)
+    assert torch.equal(view.row(5).cpu(), torch.from_numpy(ref_view.row(5).copy()))
+    # copy: test/copy.js:18-22 on the device
+    target = DeviceImage({"width": 30, "height": 30, "pixel": "rgba"})
+    small.copy(target)
+    assert target.equalPixels(small.subView(0, 0, 30, 30))
+    # throughput kernels through the handle: same tolerance as the host API; fused call = the two calls
+    big = dimg.resize({"width": 160, "height": 120})
+    assert_resize_close(big.to_host(), oracle_resize(host, 160, 120, "cubic", 0.7), False, "device image resize")
+    fused = dimg.resizeConvert({"width": 160, "height": 120, "pixel": "grey"})
+    assert fused.equalPixels(big.colorConvert({"pixel": "grey"}))
+
+
 def test_batch_chunks_same_shape_runs_into_single_launches(gpu):
     """The host batch path cuts runs of same-shape images into chunks of one launch each; shapes, strides and pinned /
     pageable buffers may change from image to image.  Results equal the single calls; launches are far fewer than images."""

@@ -263,3 +263,33 @@ def test_synthetic_host_generator_is_deterministic_and_uniform():
     assert abs(rows.mean() - 127.5) < 4 and rows.min() < 8 and rows.max() > 247
     pad = np.lib.stride_tricks.as_strided(a[192:], (31, 4), (196, 1))
     assert not pad.any()
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src")), reason="no reference checkout here")
+def test_addon_patch_applies_and_the_patched_sources_compile(tmp_path):
+    """addon/picha_b200.patch turns the reference's four call sites (src/resize.cc:293,399,
+    src/colorconvert.cc:201,288) and binding.gyp into calls of the C-ABI.  No Node toolchain exists here, so the
+    check is: the patch applies cleanly to the reference's sources, and the WHOLE patched translation units compile
+    (-fsyntax-only) against the inert v8/node/nan stand-ins the compiled oracle is built with."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    work = tmp_path / "picha"
+    work.mkdir()
+    shutil.copytree(os.path.join(REF, "src"), work / "src")
+    shutil.copy(os.path.join(REF, "binding.gyp"), work / "binding.gyp")
+    with open(os.path.join(root, "addon", "picha_b200.patch")) as f:
+        r = subprocess.run(["patch", "-p1", "--batch"], cwd=work, stdin=f, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for unit in ("resize.cc", "colorconvert.cc"):
+        text = (work / "src" / unit).read_text()
+        assert "picha_b200::" in text and ("resizeImage(rsopts, src, dst);" not in text) and ("doColorConvert(cs, src, dst);" not in text)
+        r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-I" + os.path.join(root, "oracle", "ref_shim"),
+                            "-I" + os.path.join(root, "include"), "-I" + os.path.join(root, "addon"), "-I" + str(work / "src"),
+                            str(work / "src" / unit)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    gyp = (work / "binding.gyp").read_text()
+    assert "-lpicha_b200" in gyp and "picha_b200_root" in gyp
