@@ -730,6 +730,19 @@ int sm_count() {
 	return v;
 }
 
+cudaError_t grow_dynamic_smem(const void *kernel, int bytes, SmemGrant *granted) {
+	static std::mutex mu;
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) return e;
+	if (dev < 0 || dev >= 16) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	std::lock_guard<std::mutex> g(mu);
+	if (bytes <= granted->bytes[dev]) return cudaSuccess;
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess) granted->bytes[dev] = bytes;
+	return e;
+}
+
 int max_dynamic_smem() {
 	int dev = 0, v = 0;
 	if (cudaGetDevice(&dev) != cudaSuccess) return 48 * 1024;

@@ -101,6 +101,15 @@ cudaError_t launch_synthetic_fill(const DevBatch &img, int n, uint64_t seed, uin
                                   cudaStream_t stream, int *launches);
 
 int max_dynamic_smem();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and device, and callers on several threads launch
+// the same kernel with different tile sizes: the attribute only ever grows (a launch never finds it below its own
+// need), under a lock, and stays at what was actually asked for.
+// `granted`: the caller's per-kernel state (a function-local static of the launch template), one slot per device.
+struct SmemGrant {
+	int bytes[16] = {0};
+};
+cudaError_t grow_dynamic_smem(const void *kernel, int bytes, SmemGrant *granted);
 int sm_count();   // SMs of the current device (B200: 148)
 
 // picha_b200_last_resize_kernel(): set by the launchers, read by the C-ABI layer

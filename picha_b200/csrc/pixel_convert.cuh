@@ -76,9 +76,11 @@ __device__ __forceinline__ void convert_store_as(uint8_t *d, const unsigned *v, 
 
 __host__ __device__ constexpr int pixel_bytes(int p) { return p == 0 ? 3 : p == 1 ? 4 : p == 2 ? 1 : p == 3 ? 2 : p == 4 ? 2 : p == 5 ? 4 : p == 6 ? 6 : 8; }
 
-// d: address of the destination pixel (in the destination's format).
+// d: address of the destination pixel (in the destination's format).  Out of line on purpose: inlined, the eight
+// conversions cost the resize kernels' pack stages enough registers to spill in their unfused form.
 template <int SC, bool SDEEP>
-__device__ __forceinline__ void convert_store(uint8_t *d, const unsigned *v, const FuseArgs &f) {
+__device__ __noinline__ void convert_store_call(uint8_t *d, unsigned v0, unsigned v1, unsigned v2, unsigned v3, FuseArgs f) {
+	const unsigned v[4] = {v0, v1, v2, v3};
 	switch (f.dst_pixel) {   // src/picha.h:79-92
 		case 0: convert_store_as<SC, SDEEP, 3, false>(d, v, f); break;
 		case 1: convert_store_as<SC, SDEEP, 4, false>(d, v, f); break;
@@ -89,6 +91,10 @@ __device__ __forceinline__ void convert_store(uint8_t *d, const unsigned *v, con
 		case 6: convert_store_as<SC, SDEEP, 3, true>(d, v, f); break;
 		default: convert_store_as<SC, SDEEP, 4, true>(d, v, f); break;
 	}
+}
+template <int SC, bool SDEEP>
+__device__ __forceinline__ void convert_store(uint8_t *d, const unsigned *v, const FuseArgs &f) {
+	convert_store_call<SC, SDEEP>(d, v[0], v[SC > 1 ? 1 : 0], v[SC > 2 ? 2 : 0], v[SC > 3 ? 3 : 0], f);
 }
 
 }  // namespace picha_b200

@@ -372,7 +372,9 @@ template <> struct PixelAcc<1> {
 #ifndef PICHA_DOWN_P2_INLINE
 #define PICHA_DOWN_P2_INLINE __noinline__
 #endif
-template <int C, bool DEEP, int GR>
+// FUSED: resize, then convert -- a function of its own, so that the conversion's registers (and the spills they
+// cause at the kernel's register budget) stay out of the plain resize.
+template <int C, bool DEEP, int GR, bool FUSED>
 __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	// pixels in flight per thread: 4 for even channel counts; 2 for odd ones, whose blocks hold twice as many loaded
@@ -419,8 +421,8 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 				uint32_t pv[C];
 #pragma unroll
 				for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
-				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * (a.fuse.dst_pixel < 0 ? BPP : pixel_bytes(a.fuse.dst_pixel));
-				if (a.fuse.dst_pixel >= 0) {
+				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * (FUSED ? pixel_bytes(a.fuse.dst_pixel) : BPP);
+				if (FUSED) {
 					convert_store<C, DEEP>(gp, pv, a.fuse);
 				} else if (BPP == 4 && !DEEP) {
 					const uint32_t lo = __byte_perm(pv[0], pv[1 % C], 0x0040), hi = __byte_perm(pv[2 % C], pv[3 % C], 0x0040);
@@ -461,7 +463,7 @@ struct Pass2IntArgs {
 };
 
 // RQ source pixels per output pixel, at most RQ * DX taps per output.  Lanes: 8 neighbouring blocks x 4 rows.
-template <bool DEEP, int RQ, int DX>
+template <bool DEEP, int RQ, int DX, bool FUSED>
 __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 	constexpr int U = kIntU, NW = RQ * DX, NWP = (NW + 3) & ~3, PER = U * RQ, NK = (U - 1) * RQ + NW;
 	constexpr int BPP = 4 * Depth<DEEP>::bytes;
@@ -500,7 +502,7 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 			uint32_t pv[4];
 #pragma unroll
 			for (int ch = 0; ch < 4; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
-			if (a.fuse.dst_pixel >= 0) {     // resize, then convert: stored here, in the destination's format
+			if (FUSED) {                     // resize, then convert: stored here, in the destination's format
 				if (U * i + u < a.tw)
 					convert_store<4, DEEP>(a.gbase + (long long)g * a.dstride + (long long)(U * i + u) * pixel_bytes(a.fuse.dst_pixel), pv, a.fuse);
 				continue;
@@ -512,7 +514,7 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 				px[u][0] = __byte_perm(__byte_perm(pv[0], pv[1], 0x0040), __byte_perm(pv[2], pv[3], 0x0040), 0x5410);
 			}
 		}
-		if (a.fuse.dst_pixel >= 0) continue;
+		if (FUSED) continue;
 		uint8_t *gp = a.gbase + (long long)g * a.dstride + (long long)(U * i) * BPP;
 		if (a.vec && U * i + U <= a.tw) {
 			if (DEEP) {
@@ -532,17 +534,17 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 	}
 }
 
-template <bool DEEP> __device__ __forceinline__ void pass2_int4_any(const Pass2IntArgs &a, int rq, int dx) {
+template <bool DEEP, bool FUSED> __device__ __forceinline__ void pass2_int4_any(const Pass2IntArgs &a, int rq, int dx) {
 	switch (rq * 8 + dx) {
-		case 2 * 8 + 2: pass2_int4<DEEP, 2, 2>(a); break;
-		case 2 * 8 + 4: pass2_int4<DEEP, 2, 4>(a); break;
-		case 2 * 8 + 6: pass2_int4<DEEP, 2, 6>(a); break;
-		case 3 * 8 + 2: pass2_int4<DEEP, 3, 2>(a); break;
-		case 3 * 8 + 4: pass2_int4<DEEP, 3, 4>(a); break;
-		case 3 * 8 + 6: pass2_int4<DEEP, 3, 6>(a); break;
-		case 4 * 8 + 2: pass2_int4<DEEP, 4, 2>(a); break;
-		case 4 * 8 + 4: pass2_int4<DEEP, 4, 4>(a); break;
-		default: pass2_int4<DEEP, 4, 6>(a); break;
+		case 2 * 8 + 2: pass2_int4<DEEP, 2, 2, FUSED>(a); break;
+		case 2 * 8 + 4: pass2_int4<DEEP, 2, 4, FUSED>(a); break;
+		case 2 * 8 + 6: pass2_int4<DEEP, 2, 6, FUSED>(a); break;
+		case 3 * 8 + 2: pass2_int4<DEEP, 3, 2, FUSED>(a); break;
+		case 3 * 8 + 4: pass2_int4<DEEP, 3, 4, FUSED>(a); break;
+		case 3 * 8 + 6: pass2_int4<DEEP, 3, 6, FUSED>(a); break;
+		case 4 * 8 + 2: pass2_int4<DEEP, 4, 2, FUSED>(a); break;
+		case 4 * 8 + 4: pass2_int4<DEEP, 4, 4, FUSED>(a); break;
+		default: pass2_int4<DEEP, 4, 6, FUSED>(a); break;
 	}
 }
 
@@ -553,7 +555,10 @@ template <bool DEEP> __device__ __forceinline__ void pass2_int4_any(const Pass2I
 
 // P2: 0 = general horizontal pass (pass2), 1 = integer-ratio pass for 4-channel pixels (pass2_int4).  A template
 // parameter so that each kernel links one family of callees (the registers of the row loop are what is left over).
-template <int DEPTH, bool DEEP, int C, int GR, int P2>
+// FUSED: resize, then convert (picha_b200_resize_convert) -- kernels of their own: a plain resize kernel that merely
+// CONTAINS the call of a converting horizontal pass runs 7 % slower (measured; the callee's nested call gives the
+// whole kernel a stack frame).
+template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED>
 #ifndef PICHA_DOWN_MINB8
 #define PICHA_DOWN_MINB8 4
 #endif
@@ -733,16 +738,13 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		for (int j = 0; j <= DEPTH; ++j) w[j] = vt.wt[widx + j];     // [DEPTH]: the row's event flags
 	};
 
-	Pass2Args pa;
-	pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
-	pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
-	pa.fuse = da.fuse;
-	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * (da.fuse.dst_pixel < 0 ? BPP : pixel_bytes(da.fuse.dst_pixel));
+	// (the horizontal pass's arguments are put together at the call, from kernel parameters: held in registers
+	// across the row loop they cost it a dozen registers)
+	uint8_t *const dtile = dst.base + (long long)blockIdx.z * dst.step + (long long)x0 * (FUSED ? pixel_bytes(da.fuse.dst_pixel) : BPP);
 	const uint32_t my_tmp = sbase + L.tmp + tid * 16;
 	// integer-ratio pass: where this thread's four units of an intermediate row go (one unit of padding after every
 	// 4 * rq units, counted from c0)
 	uint32_t epos[4];
-	Pass2IntArgs pi;
 	if (P2) {
 		const int per = kIntU * da.rq;
 #pragma unroll
@@ -750,10 +752,6 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			const int u = tid + NT * q, d = u - c0;
 			epos[q] = sbase + LI.tmp + kIntGuard + 16 * (u + (d >= 0 ? d / per : -1));
 		}
-		pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
-		pi.c0 = c0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
-		pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
-		pi.fuse = da.fuse;
 	}
 
 	// The row loop.  Which rows complete an output is not computed here: the host has put the number of outputs
@@ -847,18 +845,28 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			++y;
 			done = y >= y1;
 			if (gcount == GR || (done && gcount > 0)) {
-				pa.ng = gcount;
-				pa.gbase = dtile + (long long)(y - gcount) * dst.stride;
+				uint8_t *const gbase = dtile + (long long)(y - gcount) * dst.stride;
 #ifndef PICHA_DOWN_SKIP_SYNC     // (timing experiments only)
 				__syncthreads();           // the group's intermediate rows are complete
 #endif
 #ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
-				if (P2) {
+				if constexpr (P2 != 0) {
+					Pass2IntArgs pi;
+					pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
+					pi.c0 = da.rq * x0 + da.off0 - sx0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
+					pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
+					pi.fuse = da.fuse;
 					pi.ng = gcount;
-					pi.gbase = pa.gbase;
-					pass2_int4_any<DEEP>(pi, da.rq, da.dx);
+					pi.gbase = gbase;
+					pass2_int4_any<DEEP, FUSED>(pi, da.rq, da.dx);
 				} else {
-					pass2<C, DEEP, GR>(pa);
+					Pass2Args pa;
+					pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
+					pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
+					pa.fuse = da.fuse;
+					pa.ng = gcount;
+					pa.gbase = gbase;
+					pass2<C, DEEP, GR, FUSED>(pa);
 				}
 #endif
 #ifndef PICHA_DOWN_SKIP_SYNC
@@ -898,9 +906,10 @@ struct DownLaunch {
 // (griddepcontrol.launch_dependents at the top of the kernel) -- the partial last wave of each
 // launch would otherwise idle a good part of the GPU.  Every CTA ends with griddepcontrol.wait, so a
 // launch never completes before its predecessor and whatever follows in the stream sees all of them.
-template <int DEPTH, bool DEEP, int C, int GR, int P2> cudaError_t launch_group(const DownLaunch &a) {
-	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (see resize_exact.cu)
+template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED> cudaError_t launch_group(const DownLaunch &a) {
+	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2, FUSED>;
+	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
+	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), a.smem_bytes, &granted);
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
@@ -916,8 +925,12 @@ template <int DEPTH, bool DEEP, int C, int GR, int P2> cudaError_t launch_group(
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
-	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4>(a);   // (C == 4: no instantiation for other formats)
-	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0>(a) : launch_group<DEPTH, DEEP, C, 4, 0>(a);
+	if (a.da.fuse.dst_pixel >= 0) {       // (converting kernels: 4-row groups only)
+		if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, true>(a);
+		return launch_group<DEPTH, DEEP, C, 4, 0, true>(a);
+	}
+	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, false>(a);   // (C == 4: no instantiation for other formats)
+	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0, false>(a) : launch_group<DEPTH, DEEP, C, 4, 0, false>(a);
 }
 
 template <bool DEEP, int C> cudaError_t launch_depth(const DownLaunch &a) {

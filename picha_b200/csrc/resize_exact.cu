@@ -86,7 +86,8 @@ cudaError_t launch(const DevBatch &src, const DevBatch &dst, int n, const Resize
 	const size_t smem = (size_t)t.max_band_rows * t.tile_w * CH * sizeof(float);
 	if (smem > (size_t)max_dynamic_smem()) return cudaErrorInvalidValue;
 	auto kern = resize_exact_kernel<CH, DEEP>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (always the device maximum: the attribute is per function, and concurrent callers with different tile sizes would race on anything else)
+	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
+	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), (int)smem, &granted);
 	if (e != cudaSuccess) return e;
 	const int bands = (dst.height + t.band_h - 1) / t.band_h;
 	for (int z0 = 0; z0 < n; z0 += 65535) {   // gridDim.z limit

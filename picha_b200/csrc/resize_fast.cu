@@ -275,6 +275,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		}
 		dl.group = pairs > 0 && clean * 4 < pairs * 3 ? 8 : 4;
 		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 ? 8 : 4;
+		if (fuse.dst_pixel >= 0) dl.group = 4;   // the converting kernels exist for 4-row groups only
 	}
 	// 4-channel pixels at an integer ratio of 2, 3 or 4: the horizontal pass with a sliding window (pass2_int4).
 	// Every column's taps must lie in its nominal window [rq * x + off0, + rq * dx); columns that differ from the

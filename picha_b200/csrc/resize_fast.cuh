@@ -685,7 +685,8 @@ struct FastLaunch {
 
 template <int VARIANT, int DEPTH, bool DEEP, int XS> cudaError_t launch_one(const FastLaunch &a) {
 	auto kern = resize_fast_kernel<VARIANT, DEPTH, DEEP, XS>;
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (see resize_exact.cu)
+	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
+	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), a.smem_bytes, &granted);
 	if (e != cudaSuccess) return e;
 	dim3 grid((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
 	kern<<<grid, NT, a.smem_bytes, a.stream>>>(a.map, *a.dst, *a.t, *a.vt, a.channels);

@@ -77,7 +77,8 @@ __device__ __forceinline__ void issue_stage(uint32_t dst, uint32_t bar, const ui
 		if (i < rows) bulk_load(dst + i * win_bytes, src + (row0 + i) * stride, copy_bytes, bar);
 }
 
-template <int DEPTH, bool DEEP, int WPX, int C>
+// FUSED: resize, then convert (picha_b200_resize_convert); kernels of their own, see resize_down.cuh
+template <int DEPTH, bool DEEP, int WPX, int C, bool FUSED>
 __global__ void __launch_bounds__(NT, 6)
 resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant__ VTable vt, UpArgs ua) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
@@ -200,7 +201,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		--fleft;
 	};
 
-	uint8_t *const dcol = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * (ua.fuse.dst_pixel < 0 ? BPP : pixel_bytes(ua.fuse.dst_pixel));
+	uint8_t *const dcol = dst.base + (long long)blockIdx.z * dst.step + (long long)px0 * (FUSED ? pixel_bytes(ua.fuse.dst_pixel) : BPP);
 	const int npx = any ? min(NPX, dst.width - px0) : 0;
 
 	uint32_t raw[WPX * WPP];
@@ -324,7 +325,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 					q[i] = __byte_perm(lo, hi, 0x5410);
 				}
 			}
-			if (ua.fuse.dst_pixel >= 0) {
+			if (FUSED) {
 				// resize, then convert: each of the thread's pixels goes through the reference's conversion
 #pragma unroll
 				for (int p = 0; p < NPX; ++p)
@@ -382,10 +383,11 @@ struct UpLaunch {
 	cudaStream_t stream;
 };
 
-template <int DEPTH, bool DEEP, int WPX, int C> cudaError_t launch_one(const UpLaunch &a) {
-	auto kern = resize_up_kernel<DEPTH, DEEP, WPX, C>;
+template <int DEPTH, bool DEEP, int WPX, int C, bool FUSED> cudaError_t launch_one(const UpLaunch &a) {
+	auto kern = resize_up_kernel<DEPTH, DEEP, WPX, C, FUSED>;
 	const int smem_total = smem_bytes(a.ua.win_bytes);
-	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dynamic_smem());   // (see resize_exact.cu)
+	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
+	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), smem_total, &granted);
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((a.dst->width + TILE - 1) / TILE, a.bands, a.n);
@@ -401,8 +403,9 @@ template <int DEPTH, bool DEEP, int WPX, int C> cudaError_t launch_one(const UpL
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_wpx(const UpLaunch &a) {
-	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6, C>(a);
-	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8, C>(a);
+	if (a.ua.fuse.dst_pixel >= 0) return launch_one<DEPTH, DEEP, 8, C, true>(a);   // (converting kernels: the wider window only)
+	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6, C, false>(a);
+	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8, C, false>(a);
 	return cudaErrorNotSupported;
 }
 
