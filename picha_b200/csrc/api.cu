@@ -124,6 +124,7 @@ struct Plan {
 	FastAxisX fx;               // horizontal axis of the fast path (host copy, for launch planning)
 	int fast_tile_w[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
 	int fast_align_px[kNumPixels] = {1, 1, 1, 1, 1, 1, 1, 1};   // tile origins are multiples of this many source pixels
+	int fast_tile_w96[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0}, fast_tile_w128[kNumPixels] = {0, 0, 0, 0, 0, 0, 0, 0};
 	~Plan() { if (blob) cudaFree(blob); }
 };
 
@@ -314,6 +315,11 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		p->fast_align_px[px] = align_pixels(pi.bytes, 16);
 		p->fast_tile_w[px] = fy.variant == FastAxisY::kNone || !well_conditioned ? 0
 			: fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, p->fast_align_px[px], 512);
+		// the downscaling kernel's wide variants (8-bit formats, images that shrink by 2x or more)
+		if (p->fast_tile_w[px] > 0 && !pi.deep && fy.variant == FastAxisY::kDown && p->x.scale >= 2.0f) {
+			p->fast_tile_w96[px] = fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, p->fast_align_px[px], 512, 1536);
+			p->fast_tile_w128[px] = fast_tile_width(fx.first.data(), fx.count.data(), dw, pi.channels, unit, p->fast_align_px[px], 512, 2048);
+		}
 	}
 
 	CU(cudaMalloc((void **)&p->blob, blob.size() * 4));
@@ -510,6 +516,8 @@ int run_resize(Device *dev, const DevBatch &s, const DevBatch &d, int n, int tag
 	if (!(flags & PICHA_B200_EXACT) && (large || (flags & PICHA_B200_FORCE_FAST)) && plan->fast_tile_w[s.pixel] > 0) {
 		FastTables ft = plan->ft;
 		ft.tile_w = plan->fast_tile_w[s.pixel];
+		ft.tile_w96 = plan->fast_tile_w96[s.pixel];
+		ft.tile_w128 = plan->fast_tile_w128[s.pixel];
 		ft.align_px = plan->fast_align_px[s.pixel];
 		e = launch_resize_fast(s, d, n, ft, plan->fy, fuse, stream, &launches);
 		if (e == cudaErrorNotSupported) cudaGetLastError();

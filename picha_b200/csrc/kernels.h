@@ -70,6 +70,7 @@ struct FastTables {
 	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA
+	int tile_w96, tile_w128;   // the same for the downscaling kernel's 96- and 128-thread variants (0: none)
 	int align_px; // tile source origins are multiples of this many pixels (16-byte TMA start)
 	int band_h;   // output rows per CTA
 };
@@ -81,7 +82,9 @@ constexpr int kFastMaxDepth = 12;
 // Tile width (output columns, a multiple of `unit`) whose source span, counted from the tile origin
 // (the first tap's pixel rounded down to a multiple of align_px), fits one CTA row for every tile; 0 if
 // none does.
-int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap);
+// row_values: channel values of a source row one CTA holds (1024; 1536 / 2048 for the wide downscaling variants).
+int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap,
+                    int row_values = 1024);
 
 struct FastAxisY;
 

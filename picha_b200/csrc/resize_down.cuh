@@ -40,6 +40,9 @@ using fast::kMaxBands;
 using fast::kYtabMax;
 using fast::kWtMax;
 
+#ifndef PICHA_DOWN_RS
+#define PICHA_DOWN_RS 8
+#endif
 constexpr int NT = 64;             // threads per CTA
 constexpr int NV = 16;             // channel values of one source row owned by a thread
 constexpr int ROWV = NT * NV;      // values per staged row (the tile geometry of the generic kernel)
@@ -53,9 +56,16 @@ static_assert(ROWV == fast::NT * fast::NV, "tile widths are planned once for bot
 #endif
 // floats per intermediate row: the rows of a group land 4 banks apart (8 for odd channel counts, whose
 // neighbouring columns start 20 or 24 floats apart at a 7.5:1 ratio)
-__host__ __device__ constexpr int tmps(int channels, int group) {
-	return ROWV + (group == 4 && (channels & 1) ? PICHA_DOWN_ODD_PAD : 4);
+__host__ __device__ constexpr int tmps(int channels, int group, int nt = NT) {
+	return nt * NV + (group == 4 && (channels & 1) ? PICHA_DOWN_ODD_PAD : 4);
 }
+// Wider CTAs (96 or 128 threads: 8-bit formats, general horizontal pass): a tile's source span is 1536 or 2048 bytes
+// instead of 1024, for shapes where 1024-byte tiles divide the row badly (1080p rgb to 256 columns needs 8 tiles
+// of 341 pixels -- 42 % more columns than the image has -- but only 4 of 512).  A staged row then arrives as two
+// TMA boxes side by side, like the 16-bit rows of the 64-thread kernel.
+__host__ __device__ constexpr int stage_bytes(int nt) { return PICHA_DOWN_RS * 16 * nt; }
+__host__ __device__ constexpr int row_boxes(bool deep, int nt) { return deep || nt > 64 ? 2 : 1; }
+__host__ __device__ constexpr int box_bytes(bool deep, int nt) { return (deep ? 32 : 16) * nt / row_boxes(deep, nt); }
 #ifndef PICHA_DOWN_PACKED
 #define PICHA_DOWN_PACKED 1
 #endif
@@ -67,9 +77,6 @@ constexpr int NS = PICHA_DOWN_NS;  // ring stages
 #define PICHA_DOWN_PF 0
 #endif
 constexpr int PF = PICHA_DOWN_PF;  // stages prefetched into L2 beyond the ring (0: none)
-#ifndef PICHA_DOWN_RS
-#define PICHA_DOWN_RS 8
-#endif
 constexpr int STAGE_BYTES = PICHA_DOWN_RS * 1024;  // 8 rows of 1024 bytes (u8) or 4 rows of 2048 bytes (u16)
 constexpr int kVExp = 120;         // vertical weights are scaled by 2^kVExp
 // Table row of a source row: its DEPTH vertical weights in slot order, then one word of event flags (an even
@@ -92,14 +99,14 @@ struct SmemLayout {
 
 // nb: blocks of the horizontal pass (DownArgs::nb); wrows: weight rows held in shared memory (the plan's distinct
 // rows, or one per column of the tile); direct: pixels go straight to global memory (no output tile).
-__host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct) {
+__host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct, int nt = NT) {
 	SmemLayout L;
 	L.ring = 0;
-	L.tmp = L.ring + NS * STAGE_BYTES;
+	L.tmp = L.ring + NS * stage_bytes(nt);
 	// Every column runs the same nb blocks of taps; a column with a shorter window (image edges) reads on
 	// behind it with zero weights -- into the next row of the group or, from the last row, into this
 	// zeroed tail (at most 4 * nb pixels).
-	L.tmp_floats = G * tmps(channels, G) + (4 * nb * channels + 16 + 63) / 64 * 64;
+	L.tmp_floats = G * tmps(channels, G, nt) + (4 * nb * channels + 16 + 63) / 64 * 64;
 	L.out = L.tmp + L.tmp_floats * 4;
 	L.out_stride = ((tile_w * bpp + 127) / 128) * 128 + 16;
 	L.xw = L.out + (direct ? 0 : G * L.out_stride);
@@ -190,11 +197,13 @@ struct RingState {
 	uint32_t parity;
 };
 
-template <bool DEEP>
+template <bool DEEP, int NTT>
 __device__ __noinline__ RingState ring_advance(const CUtensorMap *map, uint32_t ring, uint32_t bars, RingState rs, int word0,
                                                   int row0, int img, int tid) {
 	constexpr int RSK = stage_rows(DEEP);
-	constexpr int BOXES = DEEP ? 2 : 1;          // TMA boxes are at most 256 elements wide
+	constexpr int BOXES = row_boxes(DEEP, NTT);  // TMA boxes are at most 256 elements wide
+	constexpr int BOXB = box_bytes(DEEP, NTT);
+	constexpr int STAGE_BYTES = stage_bytes(NTT);
 	const int prev = rs.slot;
 #ifdef PICHA_DOWN_NO_REFILL      // (timing experiments only: the ring is filled once and re-read; no copies, no waits)
 	if (rs.stage >= NS - 1) {
@@ -243,8 +252,8 @@ __device__ __noinline__ RingState ring_advance(const CUtensorMap *map, uint32_t 
 				"{\n\t.reg .pred q;\n\t"
 				"setp.eq.u32 q, %0, 1;\n\t"
 				"@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%3, {%4, %5, %6}], [%2];\n\t}"
-				::"r"(pending), "r"(ring + prev * STAGE_BYTES + RSK * 1024), "r"(bars + 8 * prev), "l"(map),
-				  "r"(word0 + 256), "r"(row0 + issue * RSK), "r"(img) : "memory");
+				::"r"(pending), "r"(ring + prev * STAGE_BYTES + RSK * BOXB), "r"(bars + 8 * prev), "l"(map),
+				  "r"(word0 + BOXB / 4), "r"(row0 + issue * RSK), "r"(img) : "memory");
 	}
 	if (!ok) fast::mbar_wait_a(bars + 8 * rs.slot, rs.parity);
 	return rs;
@@ -260,18 +269,18 @@ struct Pass2Args {
 };
 
 // shared-memory output tile -> global memory, 16 bytes per thread where the destination allows it
-template <int BPP> __device__ __forceinline__ void copy_out(const Pass2Args &a) {
+template <int BPP, int NTT> __device__ __forceinline__ void copy_out(const Pass2Args &a) {
 	__syncthreads();
 	const int row_bytes = a.tw * BPP;
 	const bool vec = ((reinterpret_cast<uintptr_t>(a.gbase) | (uintptr_t)a.dstride) & 15) == 0;
 	const int nvec = vec ? row_bytes >> 4 : 0;
 	const int done = nvec << 4;
-	for (int i = a.tid; i < a.ng * nvec; i += NT) {
+	for (int i = a.tid; i < a.ng * nvec; i += NTT) {
 		const int g = i / nvec, j = i - g * nvec;
 		reinterpret_cast<uint4 *>(a.gbase + (long long)g * a.dstride)[j] = lds<uint4>(a.sbase + a.outt + g * a.out_stride + 16 * j);
 	}
 	const int tail = row_bytes - done;
-	for (int i = a.tid; i < a.ng * tail; i += NT) {
+	for (int i = a.tid; i < a.ng * tail; i += NTT) {
 		const int g = i / tail, j = done + (i - g * tail);
 		a.gbase[(long long)g * a.dstride + j] = smem[a.outt + g * a.out_stride + j];
 	}
@@ -374,27 +383,19 @@ template <> struct PixelAcc<1> {
 #endif
 // FUSED: resize, then convert -- a function of its own, so that the conversion's registers (and the spills they
 // cause at the kernel's register budget) stay out of the plain resize.
-template <int C, bool DEEP, int GR, bool FUSED>
-__device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
+// U (pixel, row) items per thread, NTT items apart, their loads and FMA chains interleaved
+template <int C, bool DEEP, int GR, bool FUSED, int NTT, int U>
+__device__ __forceinline__ void pass2_items(const Pass2Args &a, int o0, int total, int g, uint32_t vrow) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
-	// pixels in flight per thread: 4 for even channel counts; 2 for odd ones, whose blocks hold twice as many loaded
-	// values (with 4 the kernel needs 236 registers, or spills at the 168 that 6 CTAs per SM allow)
-#ifndef PICHA_DOWN_P2_U
-#define PICHA_DOWN_P2_U ((C & 1) ? 2 : 4)
-#endif
-	constexpr int U = PICHA_DOWN_P2_U;
 	constexpr int GSH = GR == 8 ? 3 : 2;
-	const int total = a.tw * GR;
-	const int g = a.tid & (GR - 1);                // NT is a multiple of GR: the same row for every item
-	const uint32_t vrow = a.sbase + a.tmp + 4 * g * tmps(C, GR);
-	for (int o0 = a.tid; o0 < total; o0 += U * NT) {
+	{
 		int xx[U], off[U];
 		bool live[U];
 		uint32_t w[U], v[U];
 		PixelAcc<C> acc[U];
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
-			const int o = o0 + u * NT;
+			const int o = o0 + u * NTT;
 			live[u] = o < total && g < a.ng;
 			xx[u] = live[u] ? o >> GSH : 0;          // idle slots recompute column 0 and store nothing
 			const uint2 e = lds<uint2>(a.sbase + a.xf + 8 * xx[u]);
@@ -446,7 +447,30 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 			}
 		}
 	}
-	if (!a.direct) copy_out<BPP>(a);
+}
+
+template <int C, bool DEEP, int GR, bool FUSED, int NTT>
+__device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	// pixels in flight per thread: 4 for even channel counts; 2 for odd ones, whose blocks hold twice as many loaded
+	// values (with 4 the kernel needs 236 registers, or spills at the 168 that 6 CTAs per SM allow)
+#ifndef PICHA_DOWN_P2_U
+#define PICHA_DOWN_P2_U ((C & 1) ? 2 : 4)
+#endif
+	constexpr int U = PICHA_DOWN_P2_U;
+	const int total = a.tw * GR;
+	const int g = a.tid & (GR - 1);                // NTT is a multiple of GR: the same row for every item
+	const uint32_t vrow = a.sbase + a.tmp + 4 * g * tmps(C, GR, NTT);
+	// whole rounds of U items per thread, then the rest with as few slots as it needs (a round of idle slots costs
+	// what a full one does: with 160 items on 64 threads that was two rounds of 128 for one and a quarter)
+	const int full = total / (U * NTT) * (U * NTT);
+	int o0 = a.tid;
+	for (; o0 < full; o0 += U * NTT) pass2_items<C, DEEP, GR, FUSED, NTT, U>(a, o0, total, g, vrow);
+	const int rest = (total - full + NTT - 1) / NTT;   // slots per thread the remaining items need: 0 .. U - 1
+	if (rest > 2) pass2_items<C, DEEP, GR, FUSED, NTT, U>(a, o0, total, g, vrow);
+	else if (rest == 2) pass2_items<C, DEEP, GR, FUSED, NTT, 2>(a, o0, total, g, vrow);
+	else if (rest == 1) pass2_items<C, DEEP, GR, FUSED, NTT, 1>(a, o0, total, g, vrow);
+	if (!a.direct) copy_out<BPP, NTT>(a);
 }
 
 // ---- pass 2 for integer ratios, 4-channel pixels (see smem_layout_int) ---------------------------
@@ -558,17 +582,22 @@ template <bool DEEP, bool FUSED> __device__ __forceinline__ void pass2_int4_any(
 // FUSED: resize, then convert (picha_b200_resize_convert) -- kernels of their own: a plain resize kernel that merely
 // CONTAINS the call of a converting horizontal pass runs 7 % slower (measured; the callee's nested call gives the
 // whole kernel a stack frame).
-template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED>
+// NTT: threads per CTA (64; 96 or 128 for the wide 8-bit variants, see stage_bytes)
+template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED, int NTT>
 #ifndef PICHA_DOWN_MINB8
 #define PICHA_DOWN_MINB8 4
 #endif
-__global__ void __launch_bounds__(NT, GR == 8 ? PICHA_DOWN_MINB8 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
+__global__ void __launch_bounds__(NTT, NTT == 128 ? 3 : NTT == 96 ? 4 : GR == 8 ? PICHA_DOWN_MINB8 : PICHA_DOWN_MINB(DEPTH))   // 8-row groups: shared memory allows 4 CTAs per SM anyway
 resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTables t,
                    const __grid_constant__ VTable vt, DownArgs da) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
 	constexpr int RSK = stage_rows(DEEP);
 	constexpr int WS = weight_stride(DEPTH);     // floats per table row: DEPTH weights and the row's event flags
 	constexpr int WPT = DEEP ? 8 : 4;            // 32-bit words of a source row per thread
+	constexpr int BOXES = row_boxes(DEEP, NTT);
+	constexpr int BOXB = box_bytes(DEEP, NTT);
+	constexpr int STAGE_BYTES = stage_bytes(NTT);
+	static_assert(P2 == 0 || NTT == NT, "the integer-ratio pass is laid out for 64 threads");
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_one
 
@@ -581,7 +610,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
 
 	const bool direct = da.direct != 0;
-	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct);
+	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct, NTT);
 	const SmemLayoutInt LI = smem_layout_int(da.rq * da.dx);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
@@ -599,16 +628,15 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	if (tid == 0) {
 		for (int i = 0; i < NS; ++i) {
 			mbar_init_a(bars + 8 * i, 1);
-			mbar_init_a(bars + 8 * (NS + i), NT / 32);   // hand-back: one arrival per warp
+			mbar_init_a(bars + 8 * (NS + i), NTT / 32);   // hand-back: one arrival per warp
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		constexpr int BOXES = DEEP ? 2 : 1;
 		for (int k = 0; k < NS && k < rs.nstages; ++k) {
 			fast::mbar_expect_tx_a(bars + 8 * k, STAGE_BYTES);
 #pragma unroll
 			for (int b = 0; b < BOXES; ++b)
-				fast::tma_load_3d_a(ring + k * STAGE_BYTES + b * RSK * 1024, smap, bars + 8 * k, word0 + b * 256, rlo + k * RSK, blockIdx.z);
+				fast::tma_load_3d_a(ring + k * STAGE_BYTES + b * RSK * BOXB, smap, bars + 8 * k, word0 + b * (BOXB / 4), rlo + k * RSK, blockIdx.z);
 		}
 	}
 	// this tile's horizontal tables -> shared memory: weights scaled and duplicated (packed-FMA operands)
@@ -620,7 +648,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		// weight tables [table][output of the block][tap], zero where a column has no tap: table 0 from a regular
 		// block, 1..2 the image's first blocks, 3..5 its last ones
 		const int nw = da.rq * da.dx, nwp = (nw + 3) & ~3;
-		for (int i = tid; i < kIntTabs * kIntU * nwp; i += NT) {
+		for (int i = tid; i < kIntTabs * kIntU * nwp; i += NTT) {
 			const int tab = i / (kIntU * nwp), u = (i / nwp) % kIntU, j = i % nwp;
 			const int blk = tab == 0 ? da.nl : tab <= 2 ? tab - 1 : da.br0 + (tab - 3);
 			const int x = kIntU * blk + u;
@@ -631,12 +659,12 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			}
 			sts(sbase + LI.wtab + tab * int_tab_bytes(nw) + (u * nwp + j) * 4, w);
 		}
-		for (int i = tid; i < (kIntGuard + 4 * kIntRowBytes + 1024) / 4; i += NT) sts(sbase + LI.tmp + 4 * i, 0.0f);
+		for (int i = tid; i < (kIntGuard + 4 * kIntRowBytes + 1024) / 4; i += NTT) sts(sbase + LI.tmp + 4 * i, 0.0f);
 	} else
 	if (C & 1) {
 		constexpr int ci = C == 3;
 		const int nfl = 4 * flat_chunks(C, da.nb);
-		for (int i = tid; i < wrows * nfl; i += NT) {
+		for (int i = tid; i < wrows * nfl; i += NTT) {
 			const int row = i / nfl, j = i - row * nfl;
 			const int src = uniq ? t.xe_src[ci][row] : t.xrow[x0 + row];
 			const int off = uniq ? t.xe_off[ci][row] : ((t.xfirst[x0 + row] - sx0) * C) & 3;
@@ -646,20 +674,20 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		}
 	} else {
 		const float *wsrc = uniq ? t.xuw : t.xw + (long long)x0 * t.xstride;
-		for (int i = tid; i < wrows * da.nb * 4; i += NT) {
+		for (int i = tid; i < wrows * da.nb * 4; i += NTT) {
 			const int row = i / (da.nb * 4), k = i - row * (da.nb * 4);
 			const float w = k < t.xstride ? wsrc[(long long)row * t.xstride + k] * da.xscale : 0.0f;
 			asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
 		}
 	}
-	for (int i = tid; i < (P2 ? 0 : tw); i += NT) {
+	for (int i = tid; i < (P2 ? 0 : tw); i += NTT) {
 		// {byte offset of the column's first (aligned) float in a row, byte offset of its weight row | misalignment}
 		const int first = (t.xfirst[x0 + i] - sx0) * C, off = (C & 1) ? first & 3 : 0;
 		const int wrow = !uniq ? i : (C & 1) ? t.xe_col[C == 3][x0 + i] : t.xrow[x0 + i];
 		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"((first - off) * 4), "r"(wrow * L.xs2 * 4 + off) : "memory");
 	}
 	// padded taps multiply whatever lies behind a column's window by zero: make sure that is never a NaN
-	for (int i = tid; i < (P2 ? 0 : L.tmp_floats); i += NT) sts(sbase + L.tmp + 4 * i, 0.0f);
+	for (int i = tid; i < (P2 ? 0 : L.tmp_floats); i += NTT) sts(sbase + L.tmp + 4 * i, 0.0f);
 	__syncthreads();
 
 	// This thread's share of a staged row: four chunks of 4 values, 256 values apart (consecutive
@@ -667,20 +695,22 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	const uint32_t thread_off = DEEP ? 8 * tid : 4 * tid;
 	uint32_t faddr = 0;     // shared address of this thread's first chunk in the next row to fetch
 	auto load_row = [&](uint32_t (&w)[WPT]) {
+		// chunk q = values 4 * (tid + NTT * q) ...; rows of two boxes hold chunks 0, 1 in the first and 2, 3 in the second
 		if (DEEP) {
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
-				const uint2 v = lds<uint2>(faddr + (q >> 1) * (RSK * 1024) + (q & 1) * 512);
+				const uint2 v = lds<uint2>(faddr + (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2));
 				w[(2 * q) % WPT] = v.x; w[(2 * q + 1) % WPT] = v.y;
 			}
 		} else {
 #pragma unroll
-			for (int q = 0; q < 4; ++q) w[q] = (uint32_t)lds<int>(faddr + 256 * q);
+			for (int q = 0; q < 4; ++q)
+				w[q % WPT] = (uint32_t)lds<int>(faddr + (BOXES == 2 ? (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2) : q * (BOXB / 4)));
 		}
-		faddr += 1024;
+		faddr += BOXB;
 	};
 	auto advance = [&]() {
-		rs = ring_advance<DEEP>(smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
+		rs = ring_advance<DEEP, NTT>(smap, ring, bars, rs, word0, rlo, blockIdx.z, tid);
 		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
 	};
 
@@ -749,7 +779,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		const int per = kIntU * da.rq;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const int u = tid + NT * q, d = u - c0;
+			const int u = tid + NTT * q, d = u - c0;
 			epos[q] = sbase + LI.tmp + kIntGuard + 16 * (u + (d >= 0 ? d / per : -1));
 		}
 	}
@@ -821,7 +851,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 #if PICHA_DOWN_PACKED
 #pragma unroll
 				for (int q = 0; q < 4; ++q) {
-					const uint32_t addr = P2 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024;
+					const uint32_t addr = P2 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR, NTT) * 4) + q * (16 * NTT);
 					asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(acc[s][2 * q]), "l"(acc[s][2 * q + 1]) : "memory");
 				}
 #else
@@ -866,7 +896,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 					pa.fuse = da.fuse;
 					pa.ng = gcount;
 					pa.gbase = gbase;
-					pass2<C, DEEP, GR, FUSED>(pa);
+					pass2<C, DEEP, GR, FUSED, NTT>(pa);
 				}
 #endif
 #ifndef PICHA_DOWN_SKIP_SYNC
@@ -897,6 +927,7 @@ struct DownLaunch {
 	int n, channels, smem_bytes, bands;
 	int overlap;    // not the first launch of this resize: may start while the previous one drains
 	int group;      // output rows per pass-2 group (4 or 8)
+	int threads;    // threads per CTA: 64, or 96 / 128 (wide 8-bit variants: 4-row groups, general horizontal pass, depth <= 4)
 	cudaStream_t stream;
 };
 
@@ -906,14 +937,14 @@ struct DownLaunch {
 // (griddepcontrol.launch_dependents at the top of the kernel) -- the partial last wave of each
 // launch would otherwise idle a good part of the GPU.  Every CTA ends with griddepcontrol.wait, so a
 // launch never completes before its predecessor and whatever follows in the stream sees all of them.
-template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED> cudaError_t launch_group(const DownLaunch &a) {
-	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2, FUSED>;
+template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED, int NTT = NT> cudaError_t launch_group(const DownLaunch &a) {
+	auto kern = resize_down_kernel<DEPTH, DEEP, C, GR, P2, FUSED, NTT>;
 	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
 	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), a.smem_bytes, &granted);
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((a.dst->width + a.t->tile_w - 1) / a.t->tile_w, a.bands, a.n);
-	cfg.blockDim = dim3(NT);
+	cfg.blockDim = dim3(NTT);
 	cfg.dynamicSmemBytes = a.smem_bytes;
 	cfg.stream = a.stream;
 	cudaLaunchAttribute attr[1];
@@ -930,6 +961,10 @@ template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &
 		return launch_group<DEPTH, DEEP, C, 4, 0, true>(a);
 	}
 	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, false>(a);   // (C == 4: no instantiation for other formats)
+	// (the wide variants exist for 8-bit formats and depths up to 4 only: elsewhere the names below are the 64-thread kernel)
+	constexpr int W96 = (DEEP || DEPTH > 4) ? NT : 96, W128 = (DEEP || DEPTH > 4) ? NT : 128;
+	if (!DEEP && DEPTH <= 4 && a.threads == 96) return launch_group<DEPTH, DEEP, C, 4, 0, false, W96>(a);
+	if (!DEEP && DEPTH <= 4 && a.threads == 128) return launch_group<DEPTH, DEEP, C, 4, 0, false, W128>(a);
 	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0, false>(a) : launch_group<DEPTH, DEEP, C, 4, 0, false>(a);
 }
 

@@ -66,8 +66,8 @@ int padded_depth(int d) {   // DEPTH the kernel is instantiated with
 
 }  // namespace
 
-int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap) {
-	const int limit = NT * NV / channels;   // source pixels one CTA row holds
+int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channels, int unit, int align_px, int cap, int row_values) {
+	const int limit = row_values / channels;   // source pixels one CTA row holds
 	// Among the widths whose source span fits, take the one that keeps both passes busiest: pass 1
 	// works on all NT*NV values of the staged row whether the tile needs them or not, pass 2 on
 	// rounds of NT (pixel, row) items.  The passes are weighted by which one dominates.
@@ -94,7 +94,8 @@ int fast_tile_width(const int *xfirst, const int *xcount, int dst_w, int channel
 		if (!ok || tiles == 0) continue;
 		const double util1 = (double)span_sum / ((double)tiles * limit);
 		const int items = (tw < dst_w ? tw : dst_w) * 4;
-		const double util2 = (double)items / ((items + NT - 1) / NT * NT);
+		const int round = row_values / 16;   // granularity of the horizontal pass: one (pixel, row) item per thread
+		const double util2 = (double)items / ((items + round - 1) / round * round);
 		const double score = 1.0 / (w1 / util1 + (1.0 - w1) / util2);
 		if (score > best_score * 1.02) { best_score = score; best = tw; }   // prefer wider tiles on near-ties
 	}
@@ -197,6 +198,22 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// Downscales whose accumulator ring is at most 8 deep take the kernel of resize_down.cuh.
 	bool use_down = fy.variant == FastAxisY::kDown && depth <= down::kMaxDepth;
 	DownLaunch dl{};
+	dl.threads = down::NT;
+	if (use_down && !deep && depth <= 4 && fuse.dst_pixel < 0 && !getenv("PICHA_B200_NO_WIDE") &&
+	    !(channels == 4 && src.width % dst.width == 0 && src.width / dst.width <= 4)) {
+		// 8-bit formats: 96- or 128-thread CTAs where their tiles divide the row so much better that fewer source
+		// columns are computed in total (tiles x threads)
+		auto cost = [&](int tile_w, int threads) { return tile_w > 0 ? (long long)((dst.width + tile_w - 1) / tile_w) * threads : (1LL << 60); };
+		long long best = cost(t.tile_w, 64);
+		if (cost(t.tile_w96, 96) * 10 < best * 9) { best = cost(t.tile_w96, 96); dl.threads = 96; }
+		if (cost(t.tile_w128, 128) * 10 < best * 9 && cost(t.tile_w128, 128) < cost(t.tile_w96, 96)) dl.threads = 128;
+		if (const char *w = getenv("PICHA_B200_DOWN_THREADS")) {
+			const int want = atoi(w);
+			if (want == 64 || (want == 96 && t.tile_w96 > 0) || (want == 128 && t.tile_w128 > 0)) dl.threads = want;
+		}
+		if (dl.threads == 96) t.tile_w = t.tile_w96;
+		if (dl.threads == 128) t.tile_w = t.tile_w128;
+	}
 	if (use_down) {
 		float wmax = 0;
 		for (float w : fy.wv) wmax = std::fmax(wmax, std::fabs(w));
@@ -273,8 +290,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				clean += (channels & 1) ? (d & 1) : d == 4;
 			}
 		}
-		dl.group = pairs > 0 && clean * 4 < pairs * 3 ? 8 : 4;
-		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 ? 8 : 4;
+		dl.group = pairs > 0 && clean * 4 < pairs * 3 && dl.threads == down::NT ? 8 : 4;   // (the wide variants: 4-row groups only)
+		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 && dl.threads == down::NT ? 8 : 4;
 		if (fuse.dst_pixel >= 0) dl.group = 4;   // the converting kernels exist for 4-row groups only
 	}
 	// 4-channel pixels at an integer ratio of 2, 3 or 4: the horizontal pass with a sliding window (pass2_int4).
@@ -306,7 +323,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		}
 	}
 	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down && dl.da.rq > 0 ? down::smem_layout_int(dl.da.rq * dl.da.dx).total
-	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0).total
+	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0, dl.threads).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
 	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;
 
@@ -317,7 +334,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	cuuint64_t dims[3] = {row_words, (cuuint64_t)src.height, (cuuint64_t)n};
 	cuuint64_t strides[2] = {(cuuint64_t)src.stride, (cuuint64_t)(n > 1 ? src.step : (int64_t)src.stride * src.height)};
 	if (strides[1] & 15) strides[1] = (strides[1] + 15) & ~15ull;   // n == 1: never dereferenced
-	cuuint32_t box[3] = {256, (cuuint32_t)(use_down ? down::stage_rows(deep) : stage_rows(deep)), 1};
+	cuuint32_t box[3] = {(cuuint32_t)(use_down ? down::box_bytes(deep, dl.threads) / 4 : 256), (cuuint32_t)(use_down ? down::stage_rows(deep) : stage_rows(deep)), 1};
 	cuuint32_t estr[3] = {1, 1, 1};
 	CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, src.base, dims, strides, box, estr,
 	                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
