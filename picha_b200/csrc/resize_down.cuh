@@ -765,7 +765,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// like the data: issued right in front of their first use, the load's latency stalls every row.
 	auto load_w = [&](float (&w)[DEPTH + 1], int widx) {
 #pragma unroll
-		for (int j = 0; j <= DEPTH; ++j) w[j] = vt.wt[widx + j];     // [DEPTH]: the row's event flags
+		for (int j = 0; j <= DEPTH; ++j) w[j] = vt.wdown[widx + j];  // [DEPTH]: the row's event flags
 	};
 
 	// (the horizontal pass's arguments are put together at the call, from kernel parameters: held in registers

@@ -363,6 +363,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		const int rows = fy.cum[y1 - 1] - first_row(y0) + 1;
 		const int outs = fy.variant == 0 ? y1 - fy.ybase[first_row(y0)] : y1 - y0;
 		// (the downscaling kernel reads the weights one row ahead and may start up to depth - 1 outputs early)
+		if (use_down) return (rows + 2) * WS <= kYtabMax + kWtMax;   // (no per-output table: VTable::wdown)
 		return outs + kFastMaxDepth <= kYtabMax && ((fy.variant == 0 ? rows : outs) + 1) * WS <= kWtMax;
 	};
 	for (;;) {
@@ -420,21 +421,18 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			vt.band_ys[b] = fy.variant == 0 ? fy.ybase[first_row(y0)] : y0;
 			vt.band_n0[b] = fy.variant == 0 ? fy.cum[vt.band_ys[b]] - vt.band_rlo[b] + 1 : 0;
 		}
-		const int *ysrc = fy.variant == 0 || use_up ? fy.cum.data() : fy.lo.data();
-		for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
-		// the new kernels look one output ahead; the upscaling kernel's output loop ends on this sentinel
-		vt.ytab[ye - vt.out_base] = use_up || ye >= dh ? -1 : ysrc[ye];
-		if (use_down) {
-			// the downscaling kernel wants row counts: rows that complete output y once y - 1 is complete
-			for (int y = ye; y > vt.out_base; --y) vt.ytab[y - vt.out_base] = y < dh ? fy.cum[y] - fy.cum[y - 1] : 0;
-			vt.ytab[0] = 0;   // a band's first output takes band_n0 instead
+		if (!use_down) {
+			const int *ysrc = fy.variant == 0 || use_up ? fy.cum.data() : fy.lo.data();
+			for (int y = vt.out_base; y < ye; ++y) vt.ytab[y - vt.out_base] = ysrc[y];
+			// the upscaling kernel looks one output ahead; its output loop ends on this sentinel
+			vt.ytab[ye - vt.out_base] = use_up || ye >= dh ? -1 : ysrc[ye];
 		}
 		// weight rows are re-strided from the host table's stride to the kernel's WS
 		const int first = fy.variant == 0 ? row_lo : yb, last = fy.variant == 0 ? row_hi : ye - 1;
 		if (use_down) {
 			// slot order: the weight of row i for output y sits at y % depth; scaled by 2^kVExp
 			for (int i = first; i <= last; ++i) {
-				float *w = vt.wt + (i - first) * WS;
+				float *w = vt.wdown + (i - first) * WS;
 				for (int j = 0; j < WS; ++j) w[j] = 0.0f;
 				for (int j = 0; j < fy.depth; ++j) w[(fy.ybase[i] + j) % depth] = fy.wv[(size_t)i * fy.stride + j] * vscale;
 				// the row loop's event flags: how many outputs this row completes, and whether the row after it is the
@@ -442,6 +440,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 				const uint32_t bits = (uint32_t)fy.done[i] | ((i & (rsk - 1)) == rsk - 2 ? down::kEvStage : 0u);
 				memcpy(&w[depth], &bits, 4);
 			}
+			// the two look-ahead rows behind the last one (the block is reused from launch to launch)
+			for (int j = 0; j < 2 * WS; ++j) vt.wdown[(last + 1 - first) * WS + j] = 0.0f;
 		} else if (use_up) {
 			// slot order: source row r sits in window slot r % depth; scaled so the result lands on [0, 1]
 			for (int i = first; i <= last; ++i) {

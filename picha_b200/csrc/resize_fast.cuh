@@ -51,8 +51,14 @@ struct alignas(16) VTable {
 	int band_rhi[kMaxBands];    // last one
 	int band_ys[kMaxBands];     // kDown: output row that is open when row band_rlo arrives (<= the band's first row)
 	int band_n0[kMaxBands];     // resize_down.cuh: source rows from band_rlo that complete output band_ys
-	int ytab[kYtabMax];         // kDown: cum[out_base + i]; kUp: lo[out_base + i]
-	float wt[kWtMax];           // kDown: weights of source row row_base + i / WS; kUp: of output out_base + i / WS
+	union {
+		struct {
+			int ytab[kYtabMax];         // kDown: cum[out_base + i]; kUp: lo[out_base + i]
+			float wt[kWtMax];           // kDown: weights of source row row_base + i / WS; kUp: of output out_base + i / WS
+		};
+		// the downscaling kernel (resize_down.cuh) has no per-output table: its rows' weights and event flags use both
+		float wdown[kYtabMax + kWtMax];
+	};
 };
 static_assert(sizeof(VTable) <= 28 * 1024, "kernel parameters are limited to 32,764 bytes");
 
