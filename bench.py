@@ -269,7 +269,7 @@ def run_resize_workload(key, args, rank, world, local_rank, with_e2e=True, with_
             else:
                 barrier()
                 if rank == 0:
-                    res["e2e_sharder"] = sharder_e2e(w, args, src, tag, fwidth, world)
+                    res["e2e_sharder"] = sharder_e2e(w, args, src, tag, fwidth, world, per_gpu=128 if big else 16)
                 barrier()
     if with_latency and rank == 0 and world == 1 and "call_latency" not in res:
         res["call_latency"] = [call_latency(w, src, tag, fwidth, t, calls=4) for t in (4, 16)]

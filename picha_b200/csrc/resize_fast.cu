@@ -352,6 +352,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	const int waves = use_down || use_up ? 6 : 16;
 	long long want = ((long long)sm_count() * ctas_per_sm * waves + tiles - 1) / tiles;
 	const int max_bands = dh / 16 > 0 ? dh / 16 : 1;
+	if (const char *b = getenv("PICHA_B200_BANDS")) want = atoi(b);   // (tuning experiments)
 	if (want > max_bands) want = max_bands;
 	if (want < 1) want = 1;
 	int band_h = (int)(((dh + want - 1) / want + 7) / 8 * 8);
