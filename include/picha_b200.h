@@ -157,6 +157,15 @@ int picha_b200_color_convert_batch(int n, const picha_b200_image *srcs, picha_b2
 
 /* Page-locked host memory for image buffers (the addon's newJsImage can hand these to
  * Nan::NewBuffer): host entry points copy straight from/to it with no staging pass. */
+/* How the batch entry points split their work (pure host logic, no device needed -- exposed so that the
+ * multi-GPU plumbing can be tested on CPU): shard `index` of `shards` owns images [lo, hi) (device = -1: one shard
+ * per GPU; the reference's counterpart is many uv_queue_work items, src/resize.cc:362-364); and the
+ * chunks of same-shape images a shard is cut into, each one kernel launch.  plan_batch returns the number of
+ * chunks and fills up to `cap` entries. */
+int picha_b200_shard_range(int n, int shards, int index, int *lo, int *hi);
+int picha_b200_plan_batch(int n, const picha_b200_image *srcs, const picha_b200_image *dsts, int lanes,
+                          int *chunk_first, int *chunk_count, int cap);
+
 void *picha_b200_host_alloc(size_t bytes);
 void picha_b200_host_free(void *p);
 

@@ -77,6 +77,8 @@ SIGNATURES = {
     "picha_b200_resize_convert_device": (ctypes.c_int, [ctypes.c_int, _IMG_P, ctypes.c_int64, _IMG_P, ctypes.c_int64, ctypes.c_int,
                                                         ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                                         ctypes.c_uint, ctypes.c_void_p]),
+    "picha_b200_shard_range": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _ip, _ip]),
+    "picha_b200_plan_batch": (ctypes.c_int, [ctypes.c_int, _IMG_P, _IMG_P, ctypes.c_int, _ip, _ip, ctypes.c_int]),
     "picha_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "picha_b200_host_free": (None, [ctypes.c_void_p]),
     "picha_b200_resize_device": (ctypes.c_int, [ctypes.c_int, _IMG_P, ctypes.c_int64, _IMG_P, ctypes.c_int64,

@@ -617,6 +617,32 @@ int submit_chunk(Device *dev, Lane *lane, const Op &op, int k, const picha_b200_
 	return flush_down(k);
 }
 
+struct Chunk { int first, count; };
+
+// Runs of same-shape images cut into chunks of one kernel launch each: at least two chunks per lane when the batch
+// allows (overlap of copies and kernels), at most 32 images or ~128 MB of source per chunk.
+std::vector<Chunk> plan_chunks(int n, const picha_b200_image *srcs, const picha_b200_image *dsts, int lanes) {
+	std::vector<Chunk> chunks;
+	if (lanes < 1) lanes = 1;
+	const int by_count = n / (2 * lanes) > 0 ? n / (2 * lanes) : 1;
+	for (int i = 0; i < n;) {
+		const size_t bytes = align_up(device_pitch(srcs[i]) * (size_t)(srcs[i].height > 0 ? srcs[i].height : 0), 256);
+		const int by_bytes = bytes > 0 && (size_t(128) << 20) / bytes > 0 ? (int)((size_t(128) << 20) / bytes) : 1;
+		const int kmax = by_count < by_bytes ? (by_count < 32 ? by_count : 32) : (by_bytes < 32 ? by_bytes : 32);
+		int k = 1;
+		while (i + k < n && k < kmax && same_shape(srcs[i], srcs[i + k]) && same_shape(dsts[i], dsts[i + k])) ++k;
+		chunks.push_back(Chunk{i, k});
+		i += k;
+	}
+	return chunks;
+}
+
+// Image block of shard `index` of `shards`: contiguous, no exchange.
+void shard_range(int n, int shards, int index, int *lo, int *hi) {
+	*lo = (int)((int64_t)n * index / shards);
+	*hi = (int)((int64_t)n * (index + 1) / shards);
+}
+
 // A batch on one device: runs of same-shape images are cut into chunks, chunks go round-robin over a few lanes
 // so the copy engines and the SMs overlap (H2D of chunk c+1 with the kernel of chunk c and the D2H of chunk c-1).
 // A chunk is one kernel launch, whatever its size (the launch of a single image is a few tiles: it cannot fill
@@ -634,19 +660,7 @@ int batch_on_device(int ordinal, const Op &op, int n, const picha_b200_image *sr
 		lanes[l] = dev->acquire();
 		if (!lanes[l]) { rc = PICHA_B200_ERR_CUDA; g_last_error = "cudaStreamCreate failed"; }
 	}
-	// chunk size: at least two chunks per lane when the batch allows (overlap), at most 32 images or ~128 MB of source
-	struct Chunk { int first, count; };
-	std::vector<Chunk> chunks;
-	const int by_count = n / (2 * kLanes) > 0 ? n / (2 * kLanes) : 1;
-	for (int i = 0; i < n;) {
-		const size_t bytes = align_up(device_pitch(srcs[i]) * srcs[i].height, 256);
-		const int by_bytes = bytes > 0 && (size_t(128) << 20) / bytes > 0 ? (int)((size_t(128) << 20) / bytes) : 1;
-		const int kmax = by_count < by_bytes ? (by_count < 32 ? by_count : 32) : (by_bytes < 32 ? by_bytes : 32);
-		int k = 1;
-		while (i + k < n && k < kmax && same_shape(srcs[i], srcs[i + k]) && same_shape(dsts[i], dsts[i + k])) ++k;
-		chunks.push_back(Chunk{i, k});
-		i += k;
-	}
+	const std::vector<Chunk> chunks = plan_chunks(n, srcs, dsts, kLanes);
 	// One host thread per lane takes chunks off a shared counter: re-pitching pageable images into pinned staging
 	// memory is a host memcpy (~10 GB/s per thread), and four of them keep the copy engine busy where one cannot.
 	std::atomic<int> next{0};
@@ -709,7 +723,8 @@ int run_batch(const Op &op, int n, const picha_b200_image *srcs, picha_b200_imag
 	std::vector<std::string> errs(shards);
 	std::vector<std::thread> threads;
 	for (int s = 0; s < shards; ++s) {
-		const int lo = (int)((int64_t)n * s / shards), hi = (int)((int64_t)n * (s + 1) / shards);
+		int lo, hi;
+		shard_range(n, shards, s, &lo, &hi);
 		threads.emplace_back([&, s, lo, hi]() {
 			rcs[s] = batch_on_device(s, op, hi - lo, srcs + lo, dsts + lo);
 			if (rcs[s]) errs[s] = g_last_error;
@@ -936,6 +951,23 @@ int picha_b200_resize_convert_device(int n, const picha_b200_image *src0, int64_
 	DevBatch d = dev_batch(static_cast<uint8_t *>(dst0->data), dst_step, dst0->stride, *dst0);
 	const float luma[3] = {r, g, b};
 	return run_resize(dev, s, d, n, filter_tag, filter_width, flags, static_cast<cudaStream_t>(stream), luma);
+}
+
+int picha_b200_shard_range(int n, int shards, int index, int *lo, int *hi) {
+	if (n < 0 || shards <= 0 || index < 0 || index >= shards || !lo || !hi) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	shard_range(n, shards, index, lo, hi);
+	return 0;
+}
+
+int picha_b200_plan_batch(int n, const picha_b200_image *srcs, const picha_b200_image *dsts, int lanes,
+                          int *chunk_first, int *chunk_count, int cap) {
+	if (n < 0 || (n > 0 && (!srcs || !dsts))) return PICHA_B200_ERR_INVALID_ARGUMENT;
+	const std::vector<Chunk> chunks = plan_chunks(n, srcs, dsts, lanes);
+	for (size_t i = 0; i < chunks.size() && (int)i < cap; ++i) {
+		if (chunk_first) chunk_first[i] = chunks[i].first;
+		if (chunk_count) chunk_count[i] = chunks[i].count;
+	}
+	return (int)chunks.size();
 }
 
 void *picha_b200_host_alloc(size_t bytes) {

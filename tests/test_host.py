@@ -293,3 +293,28 @@ def test_addon_patch_applies_and_the_patched_sources_compile(tmp_path):
         assert r.returncode == 0, r.stderr
     gyp = (work / "binding.gyp").read_text()
     assert "-lpicha_b200" in gyp and "picha_b200_root" in gyp
+
+
+def test_batch_plan_chunks_same_shape_runs():
+    """csrc/api.cu plan_chunks through the C-ABI: runs of same-shape images become chunks of one launch each, at
+    least two chunks per lane when the batch allows, at most 32 images or ~128 MB of source per chunk."""
+    from picha_b200.shard import plan_batch
+    img = lambda w, h, p: N.CImage(1, w * N.lib.picha_b200_pixel_bytes(p), w, h, p)
+    # 1024 thumbnails sources (1080p rgb, 6.2 MB each): 128 MB / 6.2 MB = 21 per chunk
+    chunks = plan_batch([img(1920, 1080, 0)] * 1024, [img(256, 256, 0)] * 1024)
+    assert sum(c for _, c in chunks) == 1024 and max(c for _, c in chunks) == 21 and len(chunks) == 49
+    assert [f for f, _ in chunks] == sorted(f for f, _ in chunks) and chunks[0] == (0, 21)
+    # 32 4K images (33 MB each) over 4 lanes: two chunks per lane = 4 each, which 128 MB just allows
+    chunks = plan_batch([img(3840, 2160, 1)] * 32, [img(960, 540, 1)] * 32)
+    assert chunks == [(4 * i, 4) for i in range(8)]
+    # ... and 8K-wide images (133 MB each) go one by one
+    assert max(c for _, c in plan_batch([img(7680, 4320, 1)] * 8, [img(960, 540, 1)] * 8, lanes=1)) == 1
+    # small images: the count limit (at least 2 chunks per lane, at most 32 per chunk)
+    assert max(c for _, c in plan_batch([img(64, 64, 1)] * 1000, [img(32, 32, 1)] * 1000)) == 32
+    assert plan_batch([img(64, 64, 1)] * 16, [img(32, 32, 1)] * 16) == [(2 * i, 2) for i in range(8)]
+    # a different shape (source or destination) ends a chunk
+    srcs = [img(64, 64, 1)] * 5 + [img(65, 64, 1)] + [img(64, 64, 1)] * 4
+    dsts = [img(32, 32, 1)] * 8 + [img(33, 32, 1)] * 2
+    chunks = plan_batch(srcs, dsts, lanes=1)
+    assert chunks == [(0, 5), (5, 1), (6, 2), (8, 2)]
+    assert plan_batch([], []) == []

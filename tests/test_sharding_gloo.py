@@ -24,13 +24,20 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from picha_b200.shard import shard_range
+    from picha_b200 import _native as N
+    from picha_b200.shard import plan_batch, shard_range
     import bench
     n = 37
-    lo, hi = shard_range(n, rank, world)
+    # the batch of the 8-GPU thumbnail pipeline in small: runs of same-shape images with a few odd ones in between
+    shapes = [(1920, 1080, 0)] * 14 + [(1921, 1080, 0)] + [(1920, 1080, 0)] * 9 + [(640, 480, 1)] * 13
+    srcs = [N.CImage(1, w * N.lib.picha_b200_pixel_bytes(p), w, h, p) for (w, h, p) in shapes]
+    dsts = [N.CImage(1, 256 * N.lib.picha_b200_pixel_bytes(p), 256, 256, p) for (_, _, p) in shapes]
+    lo, hi = shard_range(n, rank, world)        # the library's own split (picha_b200_*_batch(..., device=-1))
     owned = torch.zeros(n, dtype=torch.int64)
-    owned[lo:hi] = 1
-    dist.all_reduce(owned)                      # test-only: every image is owned exactly once
+    for first, count in plan_batch(srcs[lo:hi], dsts[lo:hi]):   # ... and its chunks of one launch each
+        assert count >= 1 and len({shapes[lo + first + i] for i in range(count)}) == 1
+        owned[lo + first:lo + first + count] += 1
+    dist.all_reduce(owned)                      # test-only: every image is in exactly one chunk of one rank
     ms = bench.max_over_ranks(10.0 + rank)      # what bench.py reports as the step time
     total = bench.sum_over_ranks(hi - lo)
     q.put((rank, owned.tolist(), ms, total))
