@@ -66,8 +66,14 @@ __host__ __device__ constexpr int tmps(int channels, int group, int nt = NT) {
 __host__ __device__ constexpr int stage_bytes(int nt) { return PICHA_DOWN_RS * 16 * nt; }
 __host__ __device__ constexpr int row_boxes(bool deep, int nt) { return deep || nt > 64 ? 2 : 1; }
 __host__ __device__ constexpr int box_bytes(bool deep, int nt) { return (deep ? 32 : 16) * nt / row_boxes(deep, nt); }
-#ifndef PICHA_DOWN_PACKED
-#define PICHA_DOWN_PACKED 1
+#ifndef PICHA_DOWN_FRESH
+#define PICHA_DOWN_FRESH 1       // 0: every emit zeroes its slot itself (the round-2 loop before the `fresh` row body; for A/B builds)
+#endif
+#ifndef PICHA_DOWN_ONE_BODY
+#define PICHA_DOWN_ONE_BODY 1    // 0: the row loop unrolled over two row buffers (for A/B builds)
+#endif
+#ifndef PICHA_DOWN_COLS
+#define PICHA_DOWN_COLS 1        // 0: odd channel counts run the general horizontal pass (for A/B builds)
 #endif
 #ifndef PICHA_DOWN_NS
 #define PICHA_DOWN_NS 2
@@ -93,8 +99,11 @@ __host__ __device__ constexpr int stage_rows(bool deep) { return deep ? PICHA_DO
 // 4 * channels floats there; the host sizes nb so that the longest window plus 3 floats of misalignment fits).
 __host__ __device__ constexpr int flat_chunks(int channels, int nb) { return channels * nb; }
 
+// slots of the column-wise horizontal pass (pass2_cols): two quarter warps more than the tile has columns
+__host__ __device__ constexpr int slot_count(int tile_w) { return 8 * ((tile_w + 7) / 8 + 2); }
+
 struct SmemLayout {
-	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, bars, total;
+	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, xslots, bars, total;
 };
 
 // nb: blocks of the horizontal pass (DownArgs::nb); wrows: weight rows held in shared memory (the plan's distinct
@@ -114,7 +123,9 @@ __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, in
 	// for even channel counts, the expanded flat form (see PixelAcc<3>) for odd ones
 	L.xs2 = 4 * (((channels & 1) ? flat_chunks(channels, nb) : 2 * nb) | 1);
 	L.xf = L.xw + wrows * L.xs2 * 4;         // per column: {byte offset of the first tap in a row, of the weight row}
-	L.bars = L.xf + tile_w * 8;
+	// odd channel counts: the slots of the column-wise horizontal pass (pass2_cols)
+	L.xslots = L.xf + tile_w * 8;
+	L.bars = L.xslots + ((channels & 1) ? slot_count(tile_w) * 8 : 0);
 	L.total = L.bars + 2 * NS * 8;
 	return L;
 }
@@ -265,6 +276,7 @@ struct Pass2Args {
 	int tmp, xw, xf, outt;
 	uint8_t *gbase;        // destination of the group's first row, at the tile's first column
 	int xs2, out_stride, dstride, tw, ng, tid, direct, nb;
+	int nslots;            // pass2_cols
 	FuseArgs fuse;
 };
 
@@ -343,6 +355,21 @@ template <> struct PixelAcc<3> {
 		ffma2(p01, f0, w0); ffma2(p20, f1, w1); ffma2(p12, f2, w2);
 		ffma2(p01, f3, w3); ffma2(p20, f4, w4); ffma2(p12, f5, w5);
 	}
+	// the same with the block's weights already in registers (pass2_cols: one column, several rows)
+	static constexpr int kW = 6;
+	__device__ __forceinline__ static void weights(uint32_t w, u64 (&q)[kW]) {
+		lds_2x64(w, q[0], q[1]);
+		lds_2x64(w + 16, q[2], q[3]);
+		lds_2x64(w + 32, q[4], q[5]);
+	}
+	__device__ __forceinline__ void mac(const u64 (&q)[kW], uint32_t v) {
+		u64 f0, f1, f2, f3, f4, f5;
+		lds_2x64(v, f0, f1);
+		lds_2x64(v + 16, f2, f3);
+		lds_2x64(v + 32, f4, f5);
+		ffma2(p01, f0, q[0]); ffma2(p20, f1, q[1]); ffma2(p12, f2, q[2]);
+		ffma2(p01, f3, q[3]); ffma2(p20, f4, q[4]); ffma2(p12, f5, q[5]);
+	}
 	__device__ __forceinline__ void result(float *f, int off) const {
 		float a, b, c, d, e, g;
 		unpair(p01, a, b);
@@ -364,6 +391,14 @@ template <> struct PixelAcc<1> {
 		ffma2(p, f0, w0);
 		ffma2(q, f1, w1);
 	}
+	static constexpr int kW = 2;
+	__device__ __forceinline__ static void weights(uint32_t w, u64 (&wq)[kW]) { lds_2x64(w, wq[0], wq[1]); }
+	__device__ __forceinline__ void mac(const u64 (&wq)[kW], uint32_t v) {
+		u64 f0, f1;
+		lds_2x64(v, f0, f1);
+		ffma2(p, f0, wq[0]);
+		ffma2(q, f1, wq[1]);
+	}
 	__device__ __forceinline__ void result(float *f, int) const {
 		float a, b, c, d;
 		unpair(p, a, b);
@@ -371,6 +406,40 @@ template <> struct PixelAcc<1> {
 		f[0] = (a + b) + (c + d);
 	}
 };
+
+// One finished pixel (row g of the group, column xx of the tile): packed and stored -- straight to global memory, or into
+// the shared output tile where the destination is not aligned to the pixel's store unit.
+template <int C, bool DEEP, bool FUSED>
+__device__ __forceinline__ void put_pixel(const Pass2Args &a, const float (&f)[C], int g, int xx) {
+	constexpr int BPP = C * Depth<DEEP>::bytes;
+	if (a.direct) {
+		uint32_t pv[C];
+#pragma unroll
+		for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
+		uint8_t *gp = a.gbase + (long long)g * a.dstride + xx * (FUSED ? pixel_bytes(a.fuse.dst_pixel) : BPP);
+		if (FUSED) {
+			convert_store<C, DEEP>(gp, pv, a.fuse);
+		} else if (BPP == 4 && !DEEP) {
+			const uint32_t lo = __byte_perm(pv[0], pv[1 % C], 0x0040), hi = __byte_perm(pv[2 % C], pv[3 % C], 0x0040);
+			*reinterpret_cast<uint32_t *>(gp) = __byte_perm(lo, hi, 0x5410);
+		} else if (BPP == 4) {
+			*reinterpret_cast<uint32_t *>(gp) = __byte_perm(pv[0], pv[1 % C], 0x5410);
+		} else if (BPP == 8) {
+			*reinterpret_cast<uint2 *>(gp) = make_uint2(__byte_perm(pv[0], pv[1 % C], 0x5410), __byte_perm(pv[2 % C], pv[3 % C], 0x5410));
+		} else if (BPP == 2 && !DEEP) {
+			*reinterpret_cast<uint16_t *>(gp) = (uint16_t)__byte_perm(pv[0], pv[1 % C], 0x0040);
+		} else {
+			// 1, 3 and 6 byte pixels: channel by channel (the output of a downscale is a small part of the traffic)
+#pragma unroll
+			for (int ch = 0; ch < C; ++ch) {
+				if (DEEP) reinterpret_cast<uint16_t *>(gp)[ch] = (uint16_t)pv[ch];
+				else gp[ch] = (uint8_t)pv[ch];
+			}
+		}
+	} else {
+		fast::store_pixel<C, DEEP>(a.sbase + a.outt + g * a.out_stride + xx * BPP, f);
+	}
+}
 
 // A thread produces U output pixels at a time (same row of the group, columns NT / GR apart): their
 // loads and FMA chains interleave, which is what hides the shared-memory and FMA latencies here --
@@ -418,33 +487,7 @@ __device__ __forceinline__ void pass2_items(const Pass2Args &a, int o0, int tota
 			if (!live[u]) continue;
 			float f[C];
 			acc[u].result(f, off[u]);
-			if (a.direct) {
-				uint32_t pv[C];
-#pragma unroll
-				for (int ch = 0; ch < C; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
-				uint8_t *gp = a.gbase + (long long)g * a.dstride + xx[u] * (FUSED ? pixel_bytes(a.fuse.dst_pixel) : BPP);
-				if (FUSED) {
-					convert_store<C, DEEP>(gp, pv, a.fuse);
-				} else if (BPP == 4 && !DEEP) {
-					const uint32_t lo = __byte_perm(pv[0], pv[1 % C], 0x0040), hi = __byte_perm(pv[2 % C], pv[3 % C], 0x0040);
-					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(lo, hi, 0x5410);
-				} else if (BPP == 4) {
-					*reinterpret_cast<uint32_t *>(gp) = __byte_perm(pv[0], pv[1 % C], 0x5410);
-				} else if (BPP == 8) {
-					*reinterpret_cast<uint2 *>(gp) = make_uint2(__byte_perm(pv[0], pv[1 % C], 0x5410), __byte_perm(pv[2 % C], pv[3 % C], 0x5410));
-				} else if (BPP == 2 && !DEEP) {
-					*reinterpret_cast<uint16_t *>(gp) = (uint16_t)__byte_perm(pv[0], pv[1 % C], 0x0040);
-				} else {
-					// 1, 3 and 6 byte pixels: channel by channel (the output of a downscale is a small part of the traffic)
-#pragma unroll
-					for (int ch = 0; ch < C; ++ch) {
-						if (DEEP) reinterpret_cast<uint16_t *>(gp)[ch] = (uint16_t)pv[ch];
-						else gp[ch] = (uint8_t)pv[ch];
-					}
-				}
-			} else {
-				fast::store_pixel<C, DEEP>(a.sbase + a.outt + g * a.out_stride + xx[u] * BPP, f);
-			}
+			put_pixel<C, DEEP, FUSED>(a, f, g, xx[u]);
 		}
 	}
 }
@@ -471,6 +514,92 @@ __device__ PICHA_DOWN_P2_INLINE void pass2(Pass2Args a) {
 	else if (rest == 2) pass2_items<C, DEEP, GR, FUSED, NTT, 2>(a, o0, total, g, vrow);
 	else if (rest == 1) pass2_items<C, DEEP, GR, FUSED, NTT, 1>(a, o0, total, g, vrow);
 	if (!a.direct) copy_out<BPP, NTT>(a);
+}
+
+// ---- pass 2 by columns (odd channel counts) ------------------------------------------------------
+// A thread owns one column of the tile and produces it for every row of the group: a block of the column's weights is
+// loaded once and serves GR rows (pass2 above loads it once per pixel; for rgb at 7.5:1 the horizontal pass was bound
+// by shared-memory wavefronts, half of them weights).  The lanes of a warp are columns here, so what decides bank
+// conflicts is where the columns' windows start: the kernel's prologue deals the columns to slots such that the eight
+// lanes of a quarter warp start in eight different 16-byte bank groups (see assign_slots); slot entries are
+// {first byte of the window in a row | column << 16, byte offset of the weight row | misalignment}.
+constexpr uint32_t kNoColumn = 0xFFFFu;
+
+template <int C, bool DEEP, int GR, bool FUSED, int NTT>
+__device__ __noinline__ void pass2_cols(Pass2Args a) {
+	constexpr int BSTEP = 16 * C;                  // bytes per block: 4 * C floats of the row, as many weights
+	constexpr uint32_t ROWB = tmps(C, GR, NTT) * 4;
+	for (int sl = a.tid; sl < a.nslots; sl += NTT) {
+		const uint2 e = lds<uint2>(a.sbase + a.xf + 8 * sl);
+		const uint32_t col = e.x >> 16;            // (an empty slot computes column 0's window and stores nothing)
+		uint32_t v = a.sbase + a.tmp + (e.x & 0xFFFFu);
+		uint32_t w = a.sbase + a.xw + (e.y & ~3u);
+		const int off = e.y & 3;
+		PixelAcc<C> acc[GR];
+		for (int kb = 0; kb < a.nb; ++kb) {
+			u64 wq[PixelAcc<C>::kW];
+			PixelAcc<C>::weights(w, wq);
+#pragma unroll
+			for (int g = 0; g < GR; ++g) acc[g].mac(wq, v + g * ROWB);
+			w += BSTEP;
+			v += BSTEP;
+		}
+		if (col == kNoColumn) continue;
+#pragma unroll
+		for (int g = 0; g < GR; ++g) {
+			if (g >= a.ng) break;
+			float f[C];
+			acc[g].result(f, off);
+			put_pixel<C, DEEP, FUSED>(a, f, g, (int)col);
+		}
+	}
+	if (!a.direct) copy_out<C * Depth<DEEP>::bytes, NTT>(a);
+}
+
+// Deals the tile's columns to the slots of pass2_cols (run by one warp): the q-th column whose window starts in bank
+// group r (16-byte units modulo 8) goes to slot 8 q + r -- a quarter warp then reads eight different bank groups at
+// every step of the pass.  Residues that hold more than their share of
+// columns (a ratio that puts every window in the same group) overflow into whatever slots stay empty, conflicts and all.
+// `first` and `wrow` are what the general pass keeps per column; the slots must be initialised empty before.
+__device__ __forceinline__ void assign_slots(uint32_t slots, int nslots, uint32_t colinfo, int tw, int lane) {
+	// one warp, 32 columns at a time: a column's rank among the columns of its residue comes from 8 ballots
+	int base[8];
+#pragma unroll
+	for (int r = 0; r < 8; ++r) base[r] = 0;
+	uint32_t spilled = 0;
+	for (int x0 = 0; x0 < tw; x0 += 32) {
+		const int x = x0 + lane;
+		const bool valid = x < tw;
+		const uint2 e = lds<uint2>(colinfo + 8 * (valid ? x : 0));
+		const uint32_t res = valid ? (e.x >> 4) & 7 : 8;
+		int q = 0;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			const uint32_t m = __ballot_sync(0xFFFFFFFFu, res == (uint32_t)r);
+			if (res == (uint32_t)r) q = base[r] + __popc(m & ((1u << lane) - 1u));
+			base[r] += __popc(m);
+		}
+		const int slot = 8 * q + (int)res;
+		const bool fits = valid && slot < nslots;
+		if (fits) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + 8 * slot), "r"(e.x | ((uint32_t)x << 16)), "r"(e.y) : "memory");
+		spilled |= __ballot_sync(0xFFFFFFFFu, valid && !fits);
+	}
+	__syncwarp();
+	if (spilled && lane == 0) {
+		// (rare: a residue holds more columns than the slots have rows for it: walk the columns again, counting per
+		// residue, and drop the ones past their residue's share into whatever slots stayed empty)
+		int hole = 0;
+		for (int r = 0; r < 8; ++r) {
+			int q = 0;
+			for (int x = 0; x < tw; ++x) {
+				const uint2 e = lds<uint2>(colinfo + 8 * x);
+				if (((e.x >> 4) & 7) != (uint32_t)r) continue;
+				if (8 * q + r < nslots) { ++q; continue; }
+				while ((lds<uint2>(slots + 8 * hole).x >> 16) != kNoColumn) ++hole;
+				asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slots + 8 * hole), "r"(e.x | ((uint32_t)x << 16)), "r"(e.y) : "memory");
+			}
+		}
+	}
 }
 
 // ---- pass 2 for integer ratios, 4-channel pixels (see smem_layout_int) ---------------------------
@@ -577,7 +706,8 @@ template <bool DEEP, bool FUSED> __device__ __forceinline__ void pass2_int4_any(
 #define PICHA_DOWN_MINB(D) ((D) <= 4 ? 6 : (D) <= 6 ? 5 : 4)
 #endif
 
-// P2: 0 = general horizontal pass (pass2), 1 = integer-ratio pass for 4-channel pixels (pass2_int4).  A template
+// P2: 0 = general horizontal pass (pass2), 1 = integer-ratio pass for 4-channel pixels (pass2_int4), 2 = by columns
+// (pass2_cols, odd channel counts).  A template
 // parameter so that each kernel links one family of callees (the registers of the row loop are what is left over).
 // FUSED: resize, then convert (picha_b200_resize_convert) -- kernels of their own: a plain resize kernel that merely
 // CONTAINS the call of a converting horizontal pass runs 7 % slower (measured; the callee's nested call gives the
@@ -597,7 +727,8 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	constexpr int BOXES = row_boxes(DEEP, NTT);
 	constexpr int BOXB = box_bytes(DEEP, NTT);
 	constexpr int STAGE_BYTES = stage_bytes(NTT);
-	static_assert(P2 == 0 || NTT == NT, "the integer-ratio pass is laid out for 64 threads");
+	static_assert(P2 != 1 || NTT == NT, "the integer-ratio pass is laid out for 64 threads");
+	static_assert(P2 != 2 || ((C & 1) && GR == 4), "the column-wise pass serves odd channel counts in 4-row groups");
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_one
 
@@ -614,7 +745,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	const SmemLayoutInt LI = smem_layout_int(da.rq * da.dx);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
-	const uint32_t bars = sbase + (P2 ? LI.bars : L.bars);   // full[NS] mbarriers, then NS hand-back mbarriers
+	const uint32_t bars = sbase + (P2 == 1 ? LI.bars : L.bars);   // full[NS] mbarriers, then NS hand-back mbarriers
 	const uint32_t ring = sbase + L.ring;
 
 	RingState rs;
@@ -644,7 +775,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	const int wrows = uniq ? da.wrows : tw;
 	// integer-ratio pass: nominal first unit of the tile's first block relative to the tile origin
 	const int c0 = da.rq * x0 + da.off0 - sx0;
-	if (P2) {
+	if (P2 == 1) {
 		// weight tables [table][output of the block][tap], zero where a column has no tap: table 0 from a regular
 		// block, 1..2 the image's first blocks, 3..5 its last ones
 		const int nw = da.rq * da.dx, nwp = (nw + 3) & ~3;
@@ -680,15 +811,23 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
 		}
 	}
-	for (int i = tid; i < (P2 ? 0 : tw); i += NTT) {
+	for (int i = tid; i < (P2 == 1 ? 0 : tw); i += NTT) {
 		// {byte offset of the column's first (aligned) float in a row, byte offset of its weight row | misalignment}
 		const int first = (t.xfirst[x0 + i] - sx0) * C, off = (C & 1) ? first & 3 : 0;
 		const int wrow = !uniq ? i : (C & 1) ? t.xe_col[C == 3][x0 + i] : t.xrow[x0 + i];
 		asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xf + 8 * i), "r"((first - off) * 4), "r"(wrow * L.xs2 * 4 + off) : "memory");
 	}
 	// padded taps multiply whatever lies behind a column's window by zero: make sure that is never a NaN
-	for (int i = tid; i < (P2 ? 0 : L.tmp_floats); i += NTT) sts(sbase + L.tmp + 4 * i, 0.0f);
+	for (int i = tid; i < (P2 == 1 ? 0 : L.tmp_floats); i += NTT) sts(sbase + L.tmp + 4 * i, 0.0f);
+	const int nslots = slot_count(tw);
+	if (P2 == 2)
+		for (int i = tid; i < nslots; i += NTT)
+			asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(sbase + L.xslots + 8 * i), "r"(kNoColumn << 16), "r"(0) : "memory");
 	__syncthreads();
+	if (P2 == 2) {
+		if (tid < 32) assign_slots(sbase + L.xslots, nslots, sbase + L.xf, tw, tid);
+		__syncthreads();
+	}
 
 	// This thread's share of a staged row: four chunks of 4 values, 256 values apart (consecutive
 	// lanes read consecutive words and, in the emit, write consecutive float4s: no bank conflicts).
@@ -714,7 +853,6 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		faddr = ring + rs.slot * STAGE_BYTES + thread_off;
 	};
 
-#if PICHA_DOWN_PACKED
 	// accumulators as packed pairs: fma.rn.f32x2 takes the weight as a broadcast uniform operand
 	// (FFMA2 R, R.F32x2, UR.F32, R.F32x2) and does two MACs in two issue cycles -- the same FMA rate with
 	// half the instructions in flight
@@ -723,23 +861,20 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	for (int j = 0; j < DEPTH; ++j)
 #pragma unroll
 		for (int i = 0; i < NV / 2; ++i) acc[j][i] = 0;
-#else
-	float acc[DEPTH][NV];
-#pragma unroll
-	for (int j = 0; j < DEPTH; ++j)
-#pragma unroll
-		for (int i = 0; i < NV; ++i) acc[j][i] = 0.0f;
-#endif
 
 	// One source row into every open output row.  The value is used as the subnormal float its bits
 	// already are (see the header); weights come from the constant bank as uniform operands.
-	auto body = [&](const uint32_t (&cur)[WPT], const float (&w)[DEPTH + 1]) {
+	// fresh: the slot (or -1) whose output was emitted right before this row and whose accumulators still hold that
+	// output -- its FMAs take zero as the addend instead of the accumulator, which is what clears the slot (an emit
+	// that zeroes the slot itself costs 8 packed multiplies, and ptxas renames them around the stores: 10 more MOVs)
+	// (a plain int: the lambda is inlined and the loop over slots unrolled, so the comparison is static)
+	auto body = [&](const int FRESH, const uint32_t (&cur)[WPT], const float (&w)[DEPTH + 1]) {
 #ifdef PICHA_DOWN_SKIP_BODY      // (timing experiments only: the row loop without its arithmetic)
 		uint32_t x = __float_as_uint(w[0]);
 #pragma unroll
 		for (int i = 0; i < WPT; ++i) x ^= cur[i];
 		acc[0][0] ^= x;
-#elif PICHA_DOWN_PACKED
+#else
 #pragma unroll
 		for (int i = 0; i < NV; i += 2) {
 			uint32_t b0, b1;
@@ -747,17 +882,10 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 			else { b0 = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4440 + (i & 3)); b1 = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4441 + (i & 3)); }
 			const u64 uu = pair(__uint_as_float(b0), __uint_as_float(b1));
 #pragma unroll
-			for (int j = 0; j < DEPTH; ++j) ffma2(acc[j][i >> 1], uu, pair(w[j], w[j]));
-		}
-#else
-#pragma unroll
-		for (int i = 0; i < NV; ++i) {
-			uint32_t bits;
-			if (DEEP) bits = (i & 1) ? cur[(i >> 1) % WPT] >> 16 : cur[(i >> 1) % WPT] & 0xFFFFu;
-			else bits = __byte_perm(cur[(i >> 2) % WPT], 0, 0x4440 + (i & 3));
-			const float u = __uint_as_float(bits);
-#pragma unroll
-			for (int j = 0; j < DEPTH; ++j) acc[j][i] = fmaf(w[j], u, acc[j][i]);
+			for (int j = 0; j < DEPTH; ++j) {
+				if (j == FRESH) asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(acc[j][i >> 1]) : "l"(uu), "l"(pair(w[j], w[j])), "l"(0ull));
+				else ffma2(acc[j][i >> 1], uu, pair(w[j], w[j]));
+			}
 		}
 #endif
 	};
@@ -775,7 +903,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// integer-ratio pass: where this thread's four units of an intermediate row go (one unit of padding after every
 	// 4 * rq units, counted from c0)
 	uint32_t epos[4];
-	if (P2) {
+	if (P2 == 1) {
 		const int per = kIntU * da.rq;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
@@ -813,11 +941,53 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		for (int s = 0; s < DEPTH; ++s) {
 			if (done) break;
 			if (pending == 0) {
+#if PICHA_DOWN_FRESH
+				// The first row after the emit of slot s - 1 clears that slot on the way (`fresh` in body; at the
+				// band's start the slot is zero anyway).  Peeled, so that the slot is static; the row after it moves
+				// to ra whatever the flags say, and the loop below starts where it always did.
+				{
+					load_row(rb);
+					load_w(wb, widx);
+					widx += WS;
+					body((s + DEPTH - 1) % DEPTH, ra, wa);
+					const int f = flags(wa);
+#pragma unroll
+					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+					for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+					if (f) {
+						if (f & kEvStage) advance();
+						pending = f & kEvCount;
+					}
+				}
+				if (pending == 0)
+#endif
+#if PICHA_DOWN_ONE_BODY
+				// (one body per loop: ptxas keeps the row and its successor in the same registers anyway -- each word of
+				// the next row is loaded right behind the last use of the current one -- so a loop unrolled over two
+				// row buffers only doubles the code, and the row loop's code is what fills the instruction cache)
 				for (;;) {
 					load_row(rb);
 					load_w(wb, widx);
 					widx += WS;
-					body(ra, wa);
+					body(-1, ra, wa);
+					const int f = flags(wa);
+#pragma unroll
+					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+					for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+					if (f) {
+						if (f & kEvStage) advance();
+						pending = f & kEvCount;
+						if (pending) break;
+					}
+				}
+#else
+				for (;;) {
+					load_row(rb);
+					load_w(wb, widx);
+					widx += WS;
+					body(-1, ra, wa);
 					int f = flags(wa);
 					if (f) {
 						// (rare path: once per output and once per ring stage) continue with the current row in ra
@@ -833,7 +1003,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 					load_row(ra);
 					load_w(wa, widx);
 					widx += WS;
-					body(rb, wb);
+					body(-1, rb, wb);
 					f = flags(wb);
 					if (f) {
 						if (f & kEvStage) advance();
@@ -841,36 +1011,35 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 						if (pending) break;
 					}
 				}
+#endif
 			}
 			// emit: slot s is final; it becomes the slot of output y + DEPTH
 #ifdef PICHA_DOWN_SKIP_EMIT      // (timing experiments only)
 			if (y >= y0) ++gcount;
 			if (y == -12345)
 #endif
-			if (y >= y0) {
-#if PICHA_DOWN_PACKED
+			{
+				// (predicated stores, no branch: around a branch ptxas renames the slot's registers and moves them back)
+				const uint32_t keep = y >= y0;
 #pragma unroll
 				for (int q = 0; q < 4; ++q) {
-					const uint32_t addr = P2 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR, NTT) * 4) + q * (16 * NTT);
-					asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(acc[s][2 * q]), "l"(acc[s][2 * q + 1]) : "memory");
+					const uint32_t addr = P2 == 1 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR, NTT) * 4) + q * (16 * NTT);
+					asm volatile(
+						"{\n\t.reg .pred p;\n\t"
+						"setp.ne.u32 p, %3, 0;\n\t"
+						"@p st.shared.v2.b64 [%0], {%1, %2};\n\t}"
+						::"r"(addr), "l"(acc[s][2 * q]), "l"(acc[s][2 * q + 1]), "r"(keep) : "memory");
 				}
-#else
-#pragma unroll
-				for (int q = 0; q < 4; ++q)
-					sts(my_tmp + gcount * (tmps(C, GR) * 4) + q * 1024,
-					    make_float4(acc[s][4 * q], acc[s][4 * q + 1], acc[s][4 * q + 2], acc[s][4 * q + 3]));
-#endif
-				++gcount;
+				gcount += keep;
 			}
-			// in place (tied operand, x * 0): a plain "= 0.0f" makes new values that ptxas pairs up for CS2R and
-			// then shuffles every accumulator of the kernel between two register assignments per output row
-#if PICHA_DOWN_PACKED
+			// The slot is cleared by the next row's body (see `fresh`); only when another output follows without a row
+			// in between (the discarded outputs at a band's start, ratios below 1 row per output) is it zeroed here --
+			// in place (tied operand, x * 0): a plain "= 0" makes new values that ptxas pairs up for CS2R and then
+			// shuffles every accumulator of the kernel between two register assignments per output row.
+			if (!PICHA_DOWN_FRESH || pending != 1) {
 #pragma unroll
-			for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[s][i]) : "l"(0ull));
-#else
-#pragma unroll
-			for (int i = 0; i < NV; ++i) asm volatile("mul.f32 %0, %0, 0f00000000;" : "+f"(acc[s][i]));
-#endif
+				for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[s][i]) : "l"(0ull));
+			}
 			--pending;
 			++y;
 			done = y >= y1;
@@ -880,7 +1049,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 				__syncthreads();           // the group's intermediate rows are complete
 #endif
 #ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
-				if constexpr (P2 != 0) {
+				if constexpr (P2 == 1) {
 					Pass2IntArgs pi;
 					pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
 					pi.c0 = da.rq * x0 + da.off0 - sx0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
@@ -896,7 +1065,13 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 					pa.fuse = da.fuse;
 					pa.ng = gcount;
 					pa.gbase = gbase;
-					pass2<C, DEEP, GR, FUSED, NTT>(pa);
+					if constexpr (P2 == 2) {
+						pa.xf = L.xslots;
+						pa.nslots = nslots;
+						pass2_cols<C, DEEP, GR, FUSED, NTT>(pa);
+					} else {
+						pass2<C, DEEP, GR, FUSED, NTT>(pa);
+					}
 				}
 #endif
 #ifndef PICHA_DOWN_SKIP_SYNC
@@ -956,16 +1131,21 @@ template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED, int NTT = NT>
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
-	if (a.da.fuse.dst_pixel >= 0) {       // (converting kernels: 4-row groups only)
-		if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, true>(a);
-		return launch_group<DEPTH, DEEP, C, 4, 0, true>(a);
-	}
-	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, false>(a);   // (C == 4: no instantiation for other formats)
+	// horizontal pass of the 4-row groups: by columns for odd channel counts (pass2_cols), else the general one
+	constexpr int PC = (C & 1) && PICHA_DOWN_COLS ? 2 : 0;
 	// (the wide variants exist for 8-bit formats and depths up to 4 only: elsewhere the names below are the 64-thread kernel)
 	constexpr int W96 = (DEEP || DEPTH > 4) ? NT : 96, W128 = (DEEP || DEPTH > 4) ? NT : 128;
-	if (!DEEP && DEPTH <= 4 && a.threads == 96) return launch_group<DEPTH, DEEP, C, 4, 0, false, W96>(a);
-	if (!DEEP && DEPTH <= 4 && a.threads == 128) return launch_group<DEPTH, DEEP, C, 4, 0, false, W128>(a);
-	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0, false>(a) : launch_group<DEPTH, DEEP, C, 4, 0, false>(a);
+	const bool wide = !DEEP && DEPTH <= 4;
+	if (a.da.fuse.dst_pixel >= 0) {       // (converting kernels: 4-row groups only)
+		if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, true>(a);
+		if (wide && a.threads == 96) return launch_group<DEPTH, DEEP, C, 4, PC, true, W96>(a);
+		if (wide && a.threads == 128) return launch_group<DEPTH, DEEP, C, 4, PC, true, W128>(a);
+		return launch_group<DEPTH, DEEP, C, 4, PC, true>(a);
+	}
+	if (C == 4 && a.da.rq > 0) return launch_group<DEPTH, DEEP, C, 4, C == 4, false>(a);   // (C == 4: no instantiation for other formats)
+	if (wide && a.threads == 96) return launch_group<DEPTH, DEEP, C, 4, PC, false, W96>(a);
+	if (wide && a.threads == 128) return launch_group<DEPTH, DEEP, C, 4, PC, false, W128>(a);
+	return a.group == 8 ? launch_group<DEPTH, DEEP, C, 8, 0, false>(a) : launch_group<DEPTH, DEEP, C, 4, PC, false>(a);
 }
 
 template <bool DEEP, int C> cudaError_t launch_depth(const DownLaunch &a) {

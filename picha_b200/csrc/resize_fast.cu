@@ -199,7 +199,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	bool use_down = fy.variant == FastAxisY::kDown && depth <= down::kMaxDepth;
 	DownLaunch dl{};
 	dl.threads = down::NT;
-	if (use_down && !deep && depth <= 4 && fuse.dst_pixel < 0 && !getenv("PICHA_B200_NO_WIDE") &&
+	if (use_down && !deep && depth <= 4 && !getenv("PICHA_B200_NO_WIDE") &&
 	    !(channels == 4 && src.width % dst.width == 0 && src.width / dst.width <= 4)) {
 		// 8-bit formats: 96- or 128-thread CTAs where their tiles divide the row so much better that fewer source
 		// columns are computed in total (tiles x threads)
@@ -345,7 +345,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	// tables fit a launch's parameter block.
 	const int WS = use_down ? down::weight_stride(depth) : (depth + 3) & ~3;   // floats per row of the vertical table
 	const int dh = dst.height;
-	const int ctas_per_sm = use_down || use_up ? 6 : 4;
+	// (CTAs that fit an SM: the downscaling kernel's wide variants and its 8-row groups take more of it each)
+	const int ctas_per_sm = use_down ? (dl.threads == 128 ? 3 : dl.threads == 96 || dl.group == 8 ? 4 : 6) : use_up ? 6 : 4;
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
 	// (the new kernels have a noticeable per-CTA start-up -- tables and a zeroed intermediate in shared
 	// memory, the first stage's latency -- so they get fewer, taller bands: ~6 waves instead of ~16)
