@@ -617,7 +617,7 @@ struct Pass2IntArgs {
 
 // RQ source pixels per output pixel, at most RQ * DX taps per output.  Lanes: 8 neighbouring blocks x 4 rows.
 template <bool DEEP, int RQ, int DX, bool FUSED>
-__device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
+__device__ __forceinline__ void pass2_int4(const Pass2IntArgs &a) {
 	constexpr int U = kIntU, NW = RQ * DX, NWP = (NW + 3) & ~3, PER = U * RQ, NK = (U - 1) * RQ + NW;
 	constexpr int BPP = 4 * Depth<DEEP>::bytes;
 	const int nblk = (a.tw + U - 1) / U;
@@ -687,7 +687,10 @@ __device__ __noinline__ void pass2_int4(Pass2IntArgs a) {
 	}
 }
 
-template <bool DEEP, bool FUSED> __device__ __forceinline__ void pass2_int4_any(const Pass2IntArgs &a, int rq, int dx) {
+// One out-of-line function holds all the variants: the row loop calls it from every emit slot, and with the switch at
+// the call sites (one call per variant) each slot carried 160 instructions of dispatch -- the row loop's code is what
+// fills the instruction cache.
+template <bool DEEP, bool FUSED> __device__ __noinline__ void pass2_int4_any(Pass2IntArgs a, int rq, int dx) {
 	switch (rq * 8 + dx) {
 		case 2 * 8 + 2: pass2_int4<DEEP, 2, 2, FUSED>(a); break;
 		case 2 * 8 + 4: pass2_int4<DEEP, 2, 4, FUSED>(a); break;
