@@ -78,6 +78,37 @@ template <int N> __device__ __forceinline__ void lane_words_store(unsigned *tile
 	}
 }
 
+// The same straight from / to global memory, for formats whose pixels are 1, 2, 4 or 8 bytes: a lane's four pixels
+// are one aligned 4-, 8- or 16-byte unit (two for 8-byte pixels), consecutive lanes read consecutive units -- already
+// the fully coalesced pattern, so the shared-memory regrouping (and its 2 barriers and ~10 instructions per step of
+// an issue-bound kernel) is only needed on the sides with 3- and 6-byte pixels.
+__host__ __device__ constexpr bool direct_words(int n) { return n == 1 || n == 2 || n == 4 || n == 8; }
+template <int N> __device__ __forceinline__ void lane_words_ldg(unsigned *r, const unsigned *row, int lane) {
+	if constexpr (N % 4 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 4; ++j) {
+			const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row) + lane * (N / 4) + j);
+			r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+		}
+	} else if constexpr (N == 2) {
+		const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row) + lane);
+		r[0] = v.x; r[1] = v.y;
+	} else {
+		r[0] = __ldg(row + lane);
+	}
+}
+template <int N> __device__ __forceinline__ void lane_words_stg(unsigned *row, const unsigned *r, int lane) {
+	if constexpr (N % 4 == 0) {
+#pragma unroll
+		for (int j = 0; j < N / 4; ++j)
+			reinterpret_cast<uint4 *>(row)[lane * (N / 4) + j] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+	} else if constexpr (N == 2) {
+		reinterpret_cast<uint2 *>(row)[lane] = make_uint2(r[0], r[1]);
+	} else {
+		row[lane] = r[0];
+	}
+}
+
 template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
 __device__ __forceinline__ void convert_one_unaligned(const uint8_t *s, uint8_t *d, float rf, float gf, float bf) {
 	unsigned in[4], out[4];
@@ -88,13 +119,15 @@ __device__ __forceinline__ void convert_one_unaligned(const uint8_t *s, uint8_t 
 	for (int c = 0; c < DC; ++c) store_channel<DDEEP>(d + c * Depth<DDEEP>::bytes, out[c]);
 }
 
-template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false>
+// DIRECT: both images are 16-byte aligned; the sides whose pixels are 1, 2, 4 or 8 bytes skip the shared-memory tile
+template <int SC, bool SDEEP, int DC, bool DDEEP, bool CMYK = false, bool DIRECT = false>
 __global__ void __launch_bounds__(kWarps * 32)
 convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, float gf, float bf) {
 	constexpr int SW = SC * Depth<SDEEP>::bytes;   // source words per lane per step (= bytes per pixel)
 	constexpr int DW = DC * Depth<DDEEP>::bytes;
-	__shared__ __align__(16) unsigned tile_in[kWarps][SW * 32];
-	__shared__ __align__(16) unsigned tile_out[kWarps][DW * 32];
+	constexpr bool SDIR = DIRECT && direct_words(SW), DDIR = DIRECT && direct_words(DW);
+	__shared__ __align__(16) unsigned tile_in[kWarps][SDIR ? 4 : SW * 32];
+	__shared__ __align__(16) unsigned tile_out[kWarps][DDIR ? 4 : DW * 32];
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned *tin = tile_in[warp], *tout = tile_out[warp];
@@ -111,24 +144,30 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, fl
 		// full group: 32-bit coalesced loads, one row ahead of the row being converted
 		unsigned win[SW];
 		int y = blockIdx.y;
-		if (y < src.height) {
-			const unsigned *s32 = reinterpret_cast<const unsigned *>(simg + (long long)y * src.stride);
+		auto fetch = [&](unsigned (&w)[SW], int row) {
+			const unsigned *s32 = reinterpret_cast<const unsigned *>(simg + (long long)row * src.stride);
+			if constexpr (SDIR) {
+				lane_words_ldg<SW>(w, s32, lane);
+			} else {
 #pragma unroll
-			for (int j = 0; j < SW; ++j) win[j] = __ldg(s32 + j * 32 + lane);
-		}
+				for (int j = 0; j < SW; ++j) w[j] = __ldg(s32 + j * 32 + lane);
+			}
+		};
+		if (y < src.height) fetch(win, y);
 		for (; y < src.height; y += gridDim.y) {
 			unsigned nxt[SW];
-			if (y + (int)gridDim.y < src.height) {
-				const unsigned *s32 = reinterpret_cast<const unsigned *>(simg + (long long)(y + gridDim.y) * src.stride);
-#pragma unroll
-				for (int j = 0; j < SW; ++j) nxt[j] = __ldg(s32 + j * 32 + lane);
-			}
-			__syncwarp();   // previous step's readers are done with the tiles
-#pragma unroll
-			for (int j = 0; j < SW; ++j) tin[j * 32 + lane] = win[j];
-			__syncwarp();
+			if (y + (int)gridDim.y < src.height) fetch(nxt, y + gridDim.y);
 			unsigned mine[SW];
-			lane_words_load<SW>(mine, tin, lane);
+			if constexpr (SDIR) {
+#pragma unroll
+				for (int j = 0; j < SW; ++j) mine[j] = win[j];
+			} else {
+				__syncwarp();   // previous step's readers are done with the tiles
+#pragma unroll
+				for (int j = 0; j < SW; ++j) tin[j * 32 + lane] = win[j];
+				__syncwarp();
+				lane_words_load<SW>(mine, tin, lane);
+			}
 
 			unsigned packed[DW];
 #pragma unroll
@@ -144,11 +183,16 @@ convert_rows_kernel(DevBatch src, DevBatch dst, int groups_per_row, float rf, fl
 #pragma unroll
 				for (int c = 0; c < DC; ++c) word_put<DDEEP>(packed, p * DC + c, out[c]);
 			}
-			lane_words_store<DW>(tout, packed, lane);
-			__syncwarp();
 			unsigned *d32 = reinterpret_cast<unsigned *>(dimg + (long long)y * dst.stride);
+			if constexpr (DDIR) {
+				lane_words_stg<DW>(d32, packed, lane);
+			} else {
+				if constexpr (SDIR) __syncwarp();   // (the staged source path has synchronised already)
+				lane_words_store<DW>(tout, packed, lane);
+				__syncwarp();
 #pragma unroll
-			for (int j = 0; j < DW; ++j) d32[j * 32 + lane] = tout[j * 32 + lane];
+				for (int j = 0; j < DW; ++j) d32[j * 32 + lane] = tout[j * 32 + lane];
+			}
 #pragma unroll
 			for (int j = 0; j < SW; ++j) win[j] = nxt[j];
 		}
@@ -226,7 +270,11 @@ cudaError_t launch_pair(const DevBatch &src, const DevBatch &dst, int n, float r
 			DevBatch s = src, d = dst;
 			s.base += (long long)z0 * src.step;
 			d.base += (long long)z0 * dst.step;
-			convert_rows_kernel<SC, SDEEP, DC, DDEEP, CMYK><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
+			constexpr bool can_direct = direct_words(SC * Depth<SDEEP>::bytes) || direct_words(DC * Depth<DDEEP>::bytes);
+			if (can_direct && aligned16(src) && aligned16(dst))
+				convert_rows_kernel<SC, SDEEP, DC, DDEEP, CMYK, can_direct><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
+			else
+				convert_rows_kernel<SC, SDEEP, DC, DDEEP, CMYK><<<dim3(gx, (unsigned)gy, nz), kWarps * 32, 0, stream>>>(s, d, gpr, rf, gf, bf);
 			*launches += 1;
 		}
 		return cudaGetLastError();
