@@ -92,6 +92,31 @@ __device__ __noinline__ void convert_store_call(uint8_t *d, unsigned v0, unsigne
 		default: convert_store_as<SC, SDEEP, 4, true>(d, v, f); break;
 	}
 }
+// The same for up to N pixels `step` bytes apart (a thread's column of a row group, or its neighbouring columns): one
+// call and one dispatch on the destination format for all of them -- per pixel, the call and the switch cost more
+// than the conversion (cfg5 straight to grey: 2.40 ms per 1024 thumbnails with a call per pixel against 1.97 ms for
+// the plain resize).
+template <int SC, bool SDEEP, int DC, bool DDEEP, int N>
+__device__ __forceinline__ void convert_store_n_as(uint8_t *d, long long step, int n, const unsigned (&v)[N][4], const FuseArgs &f) {
+#pragma unroll
+	for (int i = 0; i < N; ++i)
+		if (i < n) convert_store_as<SC, SDEEP, DC, DDEEP>(d + i * step, v[i], f);
+}
+template <int SC, bool SDEEP, int N> struct PixelValues { unsigned v[N][4]; };
+template <int SC, bool SDEEP, int N>
+__device__ __noinline__ void convert_store_n_call(uint8_t *d, long long step, int n, PixelValues<SC, SDEEP, N> pv, FuseArgs f) {
+	switch (f.dst_pixel) {   // src/picha.h:79-92
+		case 0: convert_store_n_as<SC, SDEEP, 3, false, N>(d, step, n, pv.v, f); break;
+		case 1: convert_store_n_as<SC, SDEEP, 4, false, N>(d, step, n, pv.v, f); break;
+		case 2: convert_store_n_as<SC, SDEEP, 1, false, N>(d, step, n, pv.v, f); break;
+		case 3: convert_store_n_as<SC, SDEEP, 2, false, N>(d, step, n, pv.v, f); break;
+		case 4: convert_store_n_as<SC, SDEEP, 1, true, N>(d, step, n, pv.v, f); break;
+		case 5: convert_store_n_as<SC, SDEEP, 2, true, N>(d, step, n, pv.v, f); break;
+		case 6: convert_store_n_as<SC, SDEEP, 3, true, N>(d, step, n, pv.v, f); break;
+		default: convert_store_n_as<SC, SDEEP, 4, true, N>(d, step, n, pv.v, f); break;
+	}
+}
+
 template <int SC, bool SDEEP>
 __device__ __forceinline__ void convert_store(uint8_t *d, const unsigned *v, const FuseArgs &f) {
 	convert_store_call<SC, SDEEP>(d, v[0], v[SC > 1 ? 1 : 0], v[SC > 2 ? 2 : 0], v[SC > 3 ? 3 : 0], f);

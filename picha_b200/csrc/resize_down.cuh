@@ -545,12 +545,25 @@ __device__ __noinline__ void pass2_cols(Pass2Args a) {
 			v += BSTEP;
 		}
 		if (col == kNoColumn) continue;
+		if constexpr (FUSED) {
+			// resize, then convert: the column's pixels of the group in one call
+			PixelValues<C, DEEP, GR> pv;
 #pragma unroll
-		for (int g = 0; g < GR; ++g) {
-			if (g >= a.ng) break;
-			float f[C];
-			acc[g].result(f, off);
-			put_pixel<C, DEEP, FUSED>(a, f, g, (int)col);
+			for (int g = 0; g < GR; ++g) {
+				float f[C];
+				acc[g].result(f, off);
+#pragma unroll
+				for (int ch = 0; ch < 4; ++ch) pv.v[g][ch] = ch < C ? fast::pack_biased<DEEP>(f[ch % C]) : 0u;
+			}
+			convert_store_n_call<C, DEEP, GR>(a.gbase + (long long)col * pixel_bytes(a.fuse.dst_pixel), a.dstride, a.ng, pv, a.fuse);
+		} else {
+#pragma unroll
+			for (int g = 0; g < GR; ++g) {
+				if (g >= a.ng) break;
+				float f[C];
+				acc[g].result(f, off);
+				put_pixel<C, DEEP, FUSED>(a, f, g, (int)col);
+			}
 		}
 	}
 	if (!a.direct) copy_out<C * Depth<DEEP>::bytes, NTT>(a);
@@ -647,6 +660,7 @@ __device__ __forceinline__ void pass2_int4(const Pass2IntArgs &a) {
 			}
 		}
 		uint32_t px[U][DEEP ? 2 : 1];
+		PixelValues<4, DEEP, U> fpv;
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
 			float f[4];
@@ -655,9 +669,9 @@ __device__ __forceinline__ void pass2_int4(const Pass2IntArgs &a) {
 			uint32_t pv[4];
 #pragma unroll
 			for (int ch = 0; ch < 4; ++ch) pv[ch] = fast::pack_biased<DEEP>(f[ch]);
-			if (FUSED) {                     // resize, then convert: stored here, in the destination's format
-				if (U * i + u < a.tw)
-					convert_store<4, DEEP>(a.gbase + (long long)g * a.dstride + (long long)(U * i + u) * pixel_bytes(a.fuse.dst_pixel), pv, a.fuse);
+			if (FUSED) {                     // resize, then convert: stored below, in the destination's format
+#pragma unroll
+				for (int ch = 0; ch < 4; ++ch) fpv.v[u][ch] = pv[ch];
 				continue;
 			}
 			if (DEEP) {
@@ -667,7 +681,11 @@ __device__ __forceinline__ void pass2_int4(const Pass2IntArgs &a) {
 				px[u][0] = __byte_perm(__byte_perm(pv[0], pv[1], 0x0040), __byte_perm(pv[2], pv[3], 0x0040), 0x5410);
 			}
 		}
-		if (FUSED) continue;
+		if (FUSED) {
+			const int pb = pixel_bytes(a.fuse.dst_pixel);
+			convert_store_n_call<4, DEEP, U>(a.gbase + (long long)g * a.dstride + (long long)(U * i) * pb, pb, a.tw - U * i, fpv, a.fuse);
+			continue;
+		}
 		uint8_t *gp = a.gbase + (long long)g * a.dstride + (long long)(U * i) * BPP;
 		if (a.vec && U * i + U <= a.tw) {
 			if (DEEP) {
