@@ -73,7 +73,7 @@ __host__ __device__ constexpr int box_bytes(bool deep, int nt) { return (deep ? 
 #define PICHA_DOWN_ONE_BODY 1    // 0: the row loop unrolled over two row buffers (for A/B builds)
 #endif
 #ifndef PICHA_DOWN_COLS
-#define PICHA_DOWN_COLS 1        // 0: odd channel counts run the general horizontal pass (for A/B builds)
+#define PICHA_DOWN_COLS 2        // horizontal pass by columns: 2 every channel count, 1 odd ones only, 0 never (for A/B builds)
 #endif
 #ifndef PICHA_DOWN_NS
 #define PICHA_DOWN_NS 2
@@ -102,13 +102,21 @@ __host__ __device__ constexpr int flat_chunks(int channels, int nb) { return cha
 // slots of the column-wise horizontal pass (pass2_cols): two quarter warps more than the tile has columns
 __host__ __device__ constexpr int slot_count(int tile_w) { return 8 * ((tile_w + 7) / 8 + 2); }
 
+// whether a kernel with `group` rows per horizontal pass runs it by columns (launch_one)
+__host__ __device__ constexpr bool by_columns(int channels, int group) {
+	// (2-channel pixels stay with the general pass: their windows start on 8-byte boundaries, the column-wise pass
+	// would read them with 8-byte loads, and measured that is slower -- greya 3840x2160 -> 1000x562: 1.02 ms against 0.62)
+	return group == 4 && channels != 2 && (PICHA_DOWN_COLS >= 2 || ((channels & 1) && PICHA_DOWN_COLS));
+}
+
 struct SmemLayout {
 	int ring, tmp, tmp_floats, out, out_stride, xw, xs2, xf, xslots, bars, total;
 };
 
 // nb: blocks of the horizontal pass (DownArgs::nb); wrows: weight rows held in shared memory (the plan's distinct
 // rows, or one per column of the tile); direct: pixels go straight to global memory (no output tile).
-__host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct, int nt = NT) {
+// cols: the horizontal pass runs by columns (pass2_cols): even channel counts then keep one float per tap instead of a pair
+__host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, int channels, int nb, int wrows, bool direct, int nt = NT, bool cols = false) {
 	SmemLayout L;
 	L.ring = 0;
 	L.tmp = L.ring + NS * stage_bytes(nt);
@@ -121,11 +129,11 @@ __host__ __device__ inline SmemLayout smem_layout(int G, int tile_w, int bpp, in
 	L.xw = L.out + (direct ? 0 : G * L.out_stride);
 	// floats per weight row, an odd number of float4s (rows spread over the banks): duplicated weights
 	// for even channel counts, the expanded flat form (see PixelAcc<3>) for odd ones
-	L.xs2 = 4 * (((channels & 1) ? flat_chunks(channels, nb) : 2 * nb) | 1);
+	L.xs2 = 4 * (((channels & 1) ? flat_chunks(channels, nb) : cols ? nb : 2 * nb) | 1);
 	L.xf = L.xw + wrows * L.xs2 * 4;         // per column: {byte offset of the first tap in a row, of the weight row}
-	// odd channel counts: the slots of the column-wise horizontal pass (pass2_cols)
+	// the slots of the column-wise horizontal pass (pass2_cols)
 	L.xslots = L.xf + tile_w * 8;
-	L.bars = L.xslots + ((channels & 1) ? slot_count(tile_w) * 8 : 0);
+	L.bars = L.xslots + (cols ? slot_count(tile_w) * 8 : 0);
 	L.total = L.bars + 2 * NS * 8;
 	return L;
 }
@@ -317,6 +325,24 @@ template <> struct PixelAcc<4> {
 		ffma2(a01, p4, w2); ffma2(a23, p5, w2);
 		ffma2(a01, p6, w3); ffma2(a23, p7, w3);
 	}
+	// by columns (pass2_cols): the block's 4 weights come as plain floats, loaded once for all rows of the group, and
+	// enter the packed FMAs as broadcast scalars (FFMA2 R, R.F32x2, R.F32, R)
+	static constexpr int kW = 2, kWBytes = 16;
+	__device__ __forceinline__ static void weights(uint32_t w, u64 (&q)[kW]) { lds_2x64(w, q[0], q[1]); }
+	__device__ __forceinline__ void mac(const u64 (&q)[kW], uint32_t v) {
+		u64 p0, p1, p2, p3, p4, p5, p6, p7;
+		float w0, w1, w2, w3;
+		unpair(q[0], w0, w1);
+		unpair(q[1], w2, w3);
+		lds_2x64(v, p0, p1);
+		lds_2x64(v + 16, p2, p3);
+		lds_2x64(v + 32, p4, p5);
+		lds_2x64(v + 48, p6, p7);
+		ffma2(a01, p0, pair(w0, w0)); ffma2(a23, p1, pair(w0, w0));
+		ffma2(a01, p2, pair(w1, w1)); ffma2(a23, p3, pair(w1, w1));
+		ffma2(a01, p4, pair(w2, w2)); ffma2(a23, p5, pair(w2, w2));
+		ffma2(a01, p6, pair(w3, w3)); ffma2(a23, p7, pair(w3, w3));
+	}
 	__device__ __forceinline__ void result(float *f, int) const { unpair(a01, f[0], f[1]); unpair(a23, f[2], f[3]); }
 };
 template <> struct PixelAcc<2> {
@@ -328,6 +354,16 @@ template <> struct PixelAcc<2> {
 		const u64 p0 = lds_64(v), p1 = lds_64(v + 8), p2 = lds_64(v + 16), p3 = lds_64(v + 24);
 		ffma2(e, p0, w0); ffma2(od, p1, w1);
 		ffma2(e, p2, w2); ffma2(od, p3, w3);
+	}
+	static constexpr int kW = 2, kWBytes = 16;
+	__device__ __forceinline__ static void weights(uint32_t w, u64 (&q)[kW]) { lds_2x64(w, q[0], q[1]); }
+	__device__ __forceinline__ void mac(const u64 (&q)[kW], uint32_t v) {
+		float w0, w1, w2, w3;
+		unpair(q[0], w0, w1);
+		unpair(q[1], w2, w3);
+		const u64 p0 = lds_64(v), p1 = lds_64(v + 8), p2 = lds_64(v + 16), p3 = lds_64(v + 24);
+		ffma2(e, p0, pair(w0, w0)); ffma2(od, p1, pair(w1, w1));
+		ffma2(e, p2, pair(w2, w2)); ffma2(od, p3, pair(w3, w3));
 	}
 	__device__ __forceinline__ void result(float *f, int) const {
 		float e0, e1, o0, o1;
@@ -356,7 +392,7 @@ template <> struct PixelAcc<3> {
 		ffma2(p01, f3, w3); ffma2(p20, f4, w4); ffma2(p12, f5, w5);
 	}
 	// the same with the block's weights already in registers (pass2_cols: one column, several rows)
-	static constexpr int kW = 6;
+	static constexpr int kW = 6, kWBytes = 48;
 	__device__ __forceinline__ static void weights(uint32_t w, u64 (&q)[kW]) {
 		lds_2x64(w, q[0], q[1]);
 		lds_2x64(w + 16, q[2], q[3]);
@@ -391,7 +427,7 @@ template <> struct PixelAcc<1> {
 		ffma2(p, f0, w0);
 		ffma2(q, f1, w1);
 	}
-	static constexpr int kW = 2;
+	static constexpr int kW = 2, kWBytes = 16;
 	__device__ __forceinline__ static void weights(uint32_t w, u64 (&wq)[kW]) { lds_2x64(w, wq[0], wq[1]); }
 	__device__ __forceinline__ void mac(const u64 (&wq)[kW], uint32_t v) {
 		u64 f0, f1;
@@ -527,7 +563,7 @@ constexpr uint32_t kNoColumn = 0xFFFFu;
 
 template <int C, bool DEEP, int GR, bool FUSED, int NTT>
 __device__ __noinline__ void pass2_cols(Pass2Args a) {
-	constexpr int BSTEP = 16 * C;                  // bytes per block: 4 * C floats of the row, as many weights
+	constexpr int BSTEP = 16 * C;                  // bytes per block: 4 * C floats of the row (odd C: as many weights; even C: 4)
 	constexpr uint32_t ROWB = tmps(C, GR, NTT) * 4;
 	for (int sl = a.tid; sl < a.nslots; sl += NTT) {
 		const uint2 e = lds<uint2>(a.sbase + a.xf + 8 * sl);
@@ -541,7 +577,7 @@ __device__ __noinline__ void pass2_cols(Pass2Args a) {
 			PixelAcc<C>::weights(w, wq);
 #pragma unroll
 			for (int g = 0; g < GR; ++g) acc[g].mac(wq, v + g * ROWB);
-			w += BSTEP;
+			w += PixelAcc<C>::kWBytes;
 			v += BSTEP;
 		}
 		if (col == kNoColumn) continue;
@@ -749,7 +785,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	constexpr int BOXB = box_bytes(DEEP, NTT);
 	constexpr int STAGE_BYTES = stage_bytes(NTT);
 	static_assert(P2 != 1 || NTT == NT, "the integer-ratio pass is laid out for 64 threads");
-	static_assert(P2 != 2 || ((C & 1) && GR == 4), "the column-wise pass serves odd channel counts in 4-row groups");
+	static_assert(P2 != 2 || GR == 4, "the column-wise pass is written for 4-row groups");
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see launch_one
 
@@ -762,7 +798,7 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	const int rlo = vt.band_rlo[band], rhi = vt.band_rhi[band];
 
 	const bool direct = da.direct != 0;
-	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct, NTT);
+	const SmemLayout L = smem_layout(GR, t.tile_w, BPP, C, da.nb, da.wrows, direct, NTT, P2 == 2);
 	const SmemLayoutInt LI = smem_layout_int(da.rq * da.dx);
 	uint32_t sbase = smem_u32(smem);
 	asm volatile("" : "+r"(sbase));   // keep it in a register: never re-derived
@@ -814,22 +850,31 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		for (int i = tid; i < (kIntGuard + 4 * kIntRowBytes + 1024) / 4; i += NTT) sts(sbase + LI.tmp + 4 * i, 0.0f);
 	} else
 	if (C & 1) {
+		// a thread expands whole rows: zero the row, then every tap C times from its position on (one global load per
+		// tap and no index arithmetic per float: with one row per column -- ratios whose weights are not periodic -- a
+		// float-by-float fill with three dependent loads each took a third of a band's time)
 		constexpr int ci = C == 3;
-		const int nfl = 4 * flat_chunks(C, da.nb);
-		for (int i = tid; i < wrows * nfl; i += NTT) {
-			const int row = i / nfl, j = i - row * nfl;
+		const int nq = flat_chunks(C, da.nb);
+		for (int row = tid; row < wrows; row += NTT) {
 			const int src = uniq ? t.xe_src[ci][row] : t.xrow[x0 + row];
 			const int off = uniq ? t.xe_off[ci][row] : ((t.xfirst[x0 + row] - sx0) * C) & 3;
-			const int k = j - off, kk = k / C;
-			const float w = k >= 0 && kk < t.xstride ? t.xuw[(long long)src * t.xstride + kk] * da.xscale : 0.0f;
-			sts(sbase + L.xw + 4 * (row * L.xs2 + j), w);
+			const uint32_t wr = sbase + L.xw + 4 * row * L.xs2;
+			for (int q = 0; q < nq; ++q) sts(wr + 16 * q, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+			const float *ws = t.xuw + (long long)src * t.xstride;
+			for (int kk = 0; kk < t.xstride; ++kk) {
+				const float w = ws[kk] * da.xscale;
+#pragma unroll
+				for (int c = 0; c < C; ++c)
+					if (off + C * kk + c < 4 * nq) sts(wr + 4 * (off + C * kk + c), w);
+			}
 		}
 	} else {
 		const float *wsrc = uniq ? t.xuw : t.xw + (long long)x0 * t.xstride;
 		for (int i = tid; i < wrows * da.nb * 4; i += NTT) {
 			const int row = i / (da.nb * 4), k = i - row * (da.nb * 4);
 			const float w = k < t.xstride ? wsrc[(long long)row * t.xstride + k] * da.xscale : 0.0f;
-			asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
+			if (P2 == 2) sts(sbase + L.xw + 4 * (row * L.xs2 + k), w);
+			else asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(sbase + L.xw + 4 * (row * L.xs2 + 2 * k)), "f"(w) : "memory");
 		}
 	}
 	for (int i = tid; i < (P2 == 1 ? 0 : tw); i += NTT) {
@@ -1152,8 +1197,8 @@ template <int DEPTH, bool DEEP, int C, int GR, int P2, bool FUSED, int NTT = NT>
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_one(const DownLaunch &a) {
-	// horizontal pass of the 4-row groups: by columns for odd channel counts (pass2_cols), else the general one
-	constexpr int PC = (C & 1) && PICHA_DOWN_COLS ? 2 : 0;
+	// horizontal pass of the 4-row groups: by columns (pass2_cols) or the general one, see by_columns
+	constexpr int PC = by_columns(C, 4) ? 2 : 0;
 	// (the wide variants exist for 8-bit formats and depths up to 4 only: elsewhere the names below are the 64-thread kernel)
 	constexpr int W96 = (DEEP || DEPTH > 4) ? NT : 96, W128 = (DEEP || DEPTH > 4) ? NT : 128;
 	const bool wide = !DEEP && DEPTH <= 4;

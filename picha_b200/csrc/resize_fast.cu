@@ -291,6 +291,8 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			}
 		}
 		dl.group = pairs > 0 && clean * 4 < pairs * 3 && dl.threads == down::NT ? 8 : 4;   // (the wide variants: 4-row groups only)
+		// (by columns -- pass2_cols -- the lanes of a phase are dealt out by bank group: 4-row groups never conflict either)
+		if (down::by_columns(channels, 4)) dl.group = 4;
 		if (const char *g = getenv("PICHA_B200_DOWN_G")) dl.group = atoi(g) == 8 && dl.threads == down::NT ? 8 : 4;
 		if (fuse.dst_pixel >= 0) dl.group = 4;   // the converting kernels exist for 4-row groups only
 	}
@@ -323,7 +325,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		}
 	}
 	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down && dl.da.rq > 0 ? down::smem_layout_int(dl.da.rq * dl.da.dx).total
-	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0, dl.threads).total
+	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0, dl.threads, down::by_columns(channels, dl.group)).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
 	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;
 
@@ -346,7 +348,9 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 	const int WS = use_down ? down::weight_stride(depth) : (depth + 3) & ~3;   // floats per row of the vertical table
 	const int dh = dst.height;
 	// (CTAs that fit an SM: the downscaling kernel's wide variants and its 8-row groups take more of it each)
-	const int ctas_per_sm = use_down ? (dl.threads == 128 ? 3 : dl.threads == 96 || dl.group == 8 ? 4 : 6) : use_up ? 6 : 4;
+	int ctas_per_sm = use_down ? (dl.threads == 128 ? 3 : dl.threads == 96 || dl.group == 8 ? 4 : 6) : use_up ? 6 : 4;
+	// (shared memory may allow fewer: a tile that keeps one weight row per column)
+	ctas_per_sm = std::max(1, std::min(ctas_per_sm, (228 * 1024) / (smem_total + 1024)));
 	const long long tiles = (long long)((dst.width + t.tile_w - 1) / t.tile_w) * n;
 	// (the new kernels have a noticeable per-CTA start-up -- tables and a zeroed intermediate in shared
 	// memory, the first stage's latency -- so they get fewer, taller bands: ~6 waves instead of ~16)
