@@ -353,6 +353,26 @@ def test_resize_kernel_variants(gpu, monkeypatch):
         assert_resize_close(got, want, False, ("up-generic", pixel, sw, sh, dw, dh, filt, fw))
 
 
+def test_resize_column_pass_bank_groups(gpu):
+    """The downscaling kernel's horizontal pass by columns (pass2_cols) deals a tile's columns to lanes by the
+    16-byte bank group their tap window starts in.  Ratios that put EVERY window into the same group (windows 32
+    floats apart: 8:1 rgba, 32:1 grey, 32:3 rgb) overflow the slots of that group and take the fallback that fills
+    the holes; ratios one float off spread evenly.  Tiles wider and narrower than a CTA has threads."""
+    P = gpu
+    rng = np.random.default_rng(777)
+    shapes = [("rgba", 2048, 300, 256, 150, "cubic", 1.0), ("rgba", 4096, 120, 512, 60, "triangle", 1.0),
+              ("grey", 6400, 200, 200, 100, "cubic", 0.7), ("rgb", 3200, 260, 300, 130, "cubic", 0.7),
+              ("r16g16b16a16", 2048, 200, 256, 50, "mitchel", 1.0), ("r16", 3200, 128, 100, 64, "triangle", 1.0),
+              ("rgb", 3210, 260, 300, 130, "cubic", 0.7), ("grey", 1000, 400, 700, 100, "lanczos", 1.0),
+              ("rgb", 1900, 300, 1300, 150, "mitchel", 1.0), ("rgba", 1500, 300, 1100, 140, "catmulrom", 1.0)]
+    for (pixel, sw, sh, dw, dh, filt, fw) in shapes:
+        img = rand_image(rng, sw, sh, pixel)
+        want = oracle_resize(img, dw, dh, filt, fw)
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        assert P.last_resize_kernel() == 3, (pixel, sw, sh, dw, dh, P.last_resize_kernel())
+        assert_resize_close(got, want, False, ("cols", pixel, sw, sh, dw, dh, filt, fw))
+
+
 def test_resize_random_shapes(gpu):
     """tests/fuzz_parity.py with a fixed seed: random formats, filters, filter scales, strides and independent
     x / y ratios between 1:5 up and 9:1 down, default path, against the oracle."""
