@@ -125,6 +125,11 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi takes 0.1 - 1 s to print its first row and the timed region lasts tens of milliseconds:
+            # do not start timing before the sampler is actually sampling
+            deadline = time.perf_counter() + 5.0
+            while not self.rows and self.proc.poll() is None and time.perf_counter() < deadline:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
