@@ -105,7 +105,8 @@ uint64_t picha_b200_launch_count(void);
 /* Which kernel served the most recent resize launched from the calling thread (diagnostics and
  * tests; there is nothing like it in the reference): 0 none yet, 1 bit-exact kernel
  * (resize_exact.cu), 2 generic throughput kernel (resize_fast.cuh), 3 downscaling kernel with
- * 4-row groups, 4 with 8-row groups (resize_down.cuh), 5 upscaling kernel (resize_up.cuh). */
+ * 4-row groups, 4 with 8-row groups, 6 with the integer-ratio horizontal pass (resize_down.cuh), 5 upscaling kernel,
+ * 7 its wide-window variant (vertical upscale with a horizontal downscale; resize_up.cuh). */
 int picha_b200_last_resize_kernel(void);
 
 /* ---- format helpers: pixelBytes / pixelChannels / NativeImage::row_stride,

@@ -280,6 +280,12 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 	build_fast_x(p->x, fx);
 	size_t o_fxw = put_f(fx.w), o_fxfirst = put_i(fx.first), o_fxcount = put_i(fx.count);
 	size_t o_fxrow = put_i(fx.urow), o_fxuw = put_f(fx.uw);
+	// vertical upscales whose 4-column groups touch more than 8 source pixels (horizontal downscales, wide filters):
+	// the dense weight blocks of the upscaling kernel's wide-window variant (2^120 = the kernel's up::kHExp)
+	WideBlocks wide;
+	if (fy.variant == FastAxisY::kUp) build_wide_blocks(fx, dw, 64, std::ldexp(1.0f, 120), wide);
+	while (blob.size() % 4) blob.push_back(0u);      // (the kernel reads the blocks as float4)
+	size_t o_wide = put_f(wide.w);
 	FlatRows flat[2];
 	size_t o_ecol[2], o_esrc[2], o_eoff[2];
 	for (int ci = 0; ci < 2; ++ci) {
@@ -359,6 +365,7 @@ int get_plan(Device *dev, int tag, float width, int sw, int sh, int dw, int dh, 
 		p->ft.xe_col[ci] = ib + o_ecol[ci]; p->ft.xe_src[ci] = ib + o_esrc[ci]; p->ft.xe_off[ci] = ib + o_eoff[ci];
 		p->ft.xe_count[ci] = (int)flat[ci].src.size();
 	}
+	p->ft.xwide = fb + o_wide; p->ft.xwide_window = wide.window;
 	p->ft.xshort = fx.taps <= 4 ? 4 : (fx.taps <= 8 ? 8 : 0);
 
 	std::vector<std::shared_ptr<Plan>> evicted;   // released (cudaFree: a device-wide synchronisation) after the lock

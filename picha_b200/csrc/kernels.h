@@ -67,6 +67,9 @@ struct FastTables {
 	// host copies of xfirst / xcount / xw (launch planning; never dereferenced on the device)
 	const int *h_xfirst, *h_xcount, *h_xrow;
 	const float *h_xw;
+	// wide-window variant of the upscaling kernel (tables.h: WideBlocks; weights already carry the kernel's 2^kHExp)
+	const float *xwide;
+	int xwide_window;   // 0: none
 	int xshort;   // 4 or 8 when no column has more taps than that (unrolled horizontal pass), else 0
 	int depth;    // vertical accumulators / window rows the kernel is instantiated with
 	int tile_w;   // output columns per CTA

@@ -259,8 +259,13 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		}
 		float wmax = 0;
 		for (int i = 0; i < dst.width * t.xstride; ++i) wmax = std::fmax(wmax, std::fabs(host_xw[i]));
-		if (wpx > 8 || !(wmax < 128.0f)) use_up = false;
-		ul.wpx = wpx;
+		if (!(wmax < 128.0f)) use_up = false;
+		// more than 8 source pixels per 4 output columns (a horizontal downscale, a very wide filter): the wide-window
+		// variant walks the window from the plan's dense weight blocks -- plain resizes only
+		const bool wide = wpx > 8;
+		if (wide && (t.xwide_window < wpx || fuse.dst_pixel >= 0 || getenv("PICHA_B200_NO_WIDE_UP"))) use_up = false;
+		ul.wpx = wide ? 0 : wpx;
+		ul.ua.window = t.xwide_window;
 		ul.ua.win_bytes = (win_px * bpp + 15) & ~15;
 		ul.ua.hscale = std::ldexp(1.0f, up::kHExp);
 		ul.ua.fuse = fuse;
@@ -493,7 +498,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		else e = deep ? launch_fast_up_u16(a) : launch_fast_up_u8(a);
 		if (e != cudaSuccess) return e;
 		*launches += 1;
-		g_last_resize_kernel = use_up ? 5 : use_down ? (dl.da.rq > 0 ? 6 : dl.group == 8 ? 4 : 3) : 2;
+		g_last_resize_kernel = use_up ? (ul.wpx == 0 ? 7 : 5) : use_down ? (dl.da.rq > 0 ? 6 : dl.group == 8 ? 4 : 3) : 2;
 		yb = ye;
 	}
 	return use_up ? cudaSuccess : map_slot_release(slot_index, stream);

@@ -16,6 +16,11 @@
 //     constant bank (laid out by window slot: row r lives in slot r % DEPTH, so the code is the same
 //     for every row), a saturating last FMA, two more instructions per value to pack, and 16/32-byte
 //     stores of the thread's own pixels -- coalesced across the warp.
+//   * Wide-window variant (WPX = 0): when a thread's 4 outputs touch more than 8 source pixels -- a vertical upscale
+//     combined with a horizontal downscale, or very wide filters -- the horizontal pass walks the thread's window
+//     pixel by pixel (up to 64), reading the pixel from the staged row and its four weights (one per output column,
+//     zero where it is not a tap: FastTables::xwide, built with the plan) through the read-only cache; everything
+//     else is the same.  (These shapes took the bit-exact kernel before: 6 - 9 % of the roofline.)
 //   * Source rows arrive through a ring of plain bulk copies (cp.async.bulk, one per row, mbarrier
 //     completion); stages are handed back like in the downscaling kernel.
 #ifndef PICHA_B200_RESIZE_UP_CUH
@@ -49,6 +54,7 @@ constexpr int kMaxDepth = 6;
 struct UpArgs {
 	int win_bytes;     // bytes of a source row staged per tile (multiple of 16)
 	float hscale;      // 2^kHExp
+	int window;        // wide-window variant: source pixels a thread walks per row (FastTables::xwide_window)
 	FuseArgs fuse;     // resize, then convert: the pack stage stores the destination's pixel format
 };
 
@@ -78,7 +84,7 @@ __device__ __forceinline__ void issue_stage(uint32_t dst, uint32_t bar, const ui
 }
 
 // FUSED: resize, then convert (picha_b200_resize_convert); kernels of their own, see resize_down.cuh
-template <int DEPTH, bool DEEP, int WPX, int C, bool FUSED>
+template <int DEPTH, bool DEEP, int WPX_, int C, bool FUSED>
 __global__ void __launch_bounds__(NT, 6)
 resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant__ VTable vt, UpArgs ua) {
 	constexpr int BPP = C * Depth<DEEP>::bytes;
@@ -86,6 +92,8 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	constexpr int WS = DEPTH <= 4 ? 4 : 8;       // vertical weights per table row
 	// registers per staged pixel: 4-channel pixels travel as 32-bit words, the others as one zero-extended value each
 	constexpr int WPP = C == 4 ? (DEEP ? 2 : 1) : C;
+	constexpr bool WIDE = WPX_ == 0;             // the wide-window variant: no register block of weights, no raw-pixel prefetch
+	constexpr int WPX = WIDE ? 1 : WPX_;
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -124,7 +132,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	const int ws = any ? t.xfirst[px0] - sx0 : 0;           // first source pixel of the thread's window (tile-relative)
 	float wh[NPX][WPX];
 #pragma unroll
-	for (int p = 0; p < NPX; ++p) {
+	for (int p = 0; p < (WIDE ? 0 : NPX); ++p) {
 		const int px = px0 + p;
 		const bool live = px < dst.width;
 		const int f = live ? t.xfirst[px] - sx0 : 0, c = live ? t.xcount[px] : 0;
@@ -179,9 +187,11 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		fleft = RS;
 		rowaddr = ring + rs.slot * stage_bytes;
 	};
+	uint32_t curaddr = 0;   // (wide-window variant) shared address of the row being processed
 	auto load_row = [&](uint32_t (&raw)[WPX * WPP]) {
+		curaddr = rowaddr;
 #pragma unroll
-		for (int j = 0; j < WPX; ++j) {
+		for (int j = 0; j < (WIDE ? 0 : WPX); ++j) {
 			if (C == 4 && DEEP) {
 				const uint2 v = lds<uint2>(rowaddr + off[j]);
 				raw[(WPP * j) % (WPX * WPP)] = v.x; raw[(WPP * j + 1) % (WPX * WPP)] = v.y;
@@ -225,8 +235,43 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 #if PICHA_UP_PACKED
 		down::u64 h2[NV / 2];
 #endif
+		if constexpr (WIDE) {
+			// walk the window: pixel j of it carries weight w4[p] into output column p (zero where it is no tap)
 #pragma unroll
-		for (int j = 0; j < WPX; ++j) {
+			for (int i = 0; i < NV; ++i) h[i] = 0.0f;
+			const float4 *wt = reinterpret_cast<const float4 *>(t.xwide) + (long long)(any ? px0 / NPX : 0) * ua.window;
+			const uint32_t base = curaddr + ws * BPP, last = curaddr + copy_bytes - BPP;
+#pragma unroll 4
+			for (int j = 0; j < ua.window; ++j) {
+				const float4 w4 = __ldg(wt + j);
+				const uint32_t a = min(base + j * BPP, last);   // (pixels behind the staged bytes carry zero weights)
+				float u[C];
+				if (C == 4 && DEEP) {
+					const uint2 v = lds<uint2>(a);
+					u[0] = __uint_as_float(v.x & 0xFFFFu); u[1 % C] = __uint_as_float(v.x >> 16);
+					u[2 % C] = __uint_as_float(v.y & 0xFFFFu); u[3 % C] = __uint_as_float(v.y >> 16);
+				} else if (C == 4) {
+					const uint32_t v = (uint32_t)lds<int>(a);
+#pragma unroll
+					for (int c = 0; c < C; ++c) u[c] = __uint_as_float(__byte_perm(v, 0, 0x4440 + c));
+				} else {
+#pragma unroll
+					for (int c = 0; c < C; ++c) {
+						uint32_t v;
+						if (DEEP) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a + 2 * c) : "memory");
+						else asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a + c) : "memory");
+						u[c] = __uint_as_float(v);
+					}
+				}
+				const float wp[NPX] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+				for (int p = 0; p < NPX; ++p)
+#pragma unroll
+					for (int c = 0; c < C; ++c) h[C * p + c] = fmaf(wp[p], u[c], h[C * p + c]);
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < (WIDE ? 0 : WPX); ++j) {
 			float u[C];
 			if (C == 4 && DEEP) {
 				u[0] = __uint_as_float(raw[(2 * j) % (WPX * WPP)] & 0xFFFFu);
@@ -267,7 +312,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		}
 #if PICHA_UP_PACKED
 #pragma unroll
-		for (int i = 0; i < NV / 2; ++i) wrow[i] = C % 2 == 0 ? h2[i] : down::pair(h[2 * i], h[2 * i + 1]);
+		for (int i = 0; i < NV / 2; ++i) wrow[i] = (C % 2 == 0 && !WIDE) ? h2[i] : down::pair(h[2 * i], h[2 * i + 1]);
 #else
 #pragma unroll
 		for (int i = 0; i < NV; ++i) wrow[i] = h[i];
@@ -379,7 +424,7 @@ struct UpLaunch {
 	const FastTables *t;
 	const VTable *vt;
 	UpArgs ua;
-	int n, bands, wpx, overlap;
+	int n, bands, wpx, overlap;   // wpx = 0: the wide-window variant
 	cudaStream_t stream;
 };
 
@@ -403,6 +448,7 @@ template <int DEPTH, bool DEEP, int WPX, int C, bool FUSED> cudaError_t launch_o
 }
 
 template <int DEPTH, bool DEEP, int C> cudaError_t launch_wpx(const UpLaunch &a) {
+	if (a.wpx == 0) return launch_one<DEPTH, DEEP, 0, C, false>(a);                 // (wide window: no converting kernels)
 	if (a.ua.fuse.dst_pixel >= 0) return launch_one<DEPTH, DEEP, 8, C, true>(a);   // (converting kernels: the wider window only)
 	if (a.wpx <= 6) return launch_one<DEPTH, DEEP, 6, C, false>(a);
 	if (a.wpx <= 8) return launch_one<DEPTH, DEEP, 8, C, false>(a);

@@ -1,6 +1,7 @@
 // See tables.h.  Compiled with -ffp-contract=off: the reference build has no FMA.
 #include "tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -241,6 +242,31 @@ void build_flat_rows(const FastAxisX &x, int channels, FlatRows &f) {
 			f.off.push_back(key.second);
 		}
 		f.col[i] = it->second;
+	}
+}
+
+void build_wide_blocks(const FastAxisX &x, int dst_size, int cap, float scale, WideBlocks &out) {
+	out.window = 0;
+	out.w.clear();
+	const int groups = (dst_size + 3) / 4;
+	int window = 0;
+	for (int g = 0; g < groups; ++g) {
+		const int lo = x.first[4 * g];
+		for (int px = 4 * g; px < dst_size && px < 4 * g + 4; ++px) {
+			if (x.first[px] < lo) return;              // the walk is anchored at the group's first column
+			window = std::max(window, x.first[px] + x.count[px] - lo);
+		}
+	}
+	if (window <= 0 || window > cap) return;
+	out.window = window;
+	out.w.assign((size_t)groups * window * 4, 0.0f);
+	for (int g = 0; g < groups; ++g) {
+		const int lo = x.first[4 * g];
+		for (int p = 0; p < 4 && 4 * g + p < dst_size; ++p) {
+			const int px = 4 * g + p;
+			for (int k = 0; k < x.count[px]; ++k)
+				out.w[((size_t)g * window + (x.first[px] - lo + k)) * 4 + p] = x.w[(size_t)px * x.stride + k] * scale;
+		}
 	}
 }
 

@@ -85,6 +85,16 @@ struct FlatRows {
 };
 void build_flat_rows(const FastAxisX &x, int channels, FlatRows &out);
 
+// Upscaling kernel, wide-window variant (csrc/resize_up.cuh, WPX = 0): a thread owns 4 consecutive output columns and
+// walks the source pixels [first[4g], first[4g] + window) of every row; block g holds, for each of those pixels, the
+// weight it carries into each of the 4 columns (zero where it is not one of the column's taps), scaled by `scale`.
+// window = 0: no such table (some group's pixels do not start at its first column's, or the widest group exceeds cap).
+struct WideBlocks {
+	int window = 0;
+	std::vector<float> w;   // [(dst + 3) / 4][window][4]
+};
+void build_wide_blocks(const FastAxisX &x, int dst_size, int cap, float scale, WideBlocks &out);
+
 // Filter tag order: src/resize.cc:151-160.  `width` is ResizeOptions::width (ScaledFilter scale).
 void build_axis(int filter_tag, float width, int src_size, int dst_size, AxisTable &out);
 

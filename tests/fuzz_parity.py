@@ -57,6 +57,6 @@ for i in range(cases):
     if not ok:
         bad += 1
         print("OUT OF TOLERANCE", pixel, sw, sh, "->", dw, dh, filt, fw, "stride", stride, "kernel", k, "max", int(d.max()), "mean", float(d.mean()))
-print("cases by kernel (1 exact, 2 generic, 3/4 down, 5 up, 6 down with the integer-ratio pass):", dict(sorted(served.items())),
+print("cases by kernel (1 exact, 2 generic, 3/4 down, 5 up, 6 down with the integer-ratio pass, 7 up with the wide window):", dict(sorted(served.items())),
       "unsupported:", unsupported, "bad:", bad)
 sys.exit(1 if bad else 0)

@@ -353,6 +353,36 @@ def test_resize_kernel_variants(gpu, monkeypatch):
         assert_resize_close(got, want, False, ("up-generic", pixel, sw, sh, dw, dh, filt, fw))
 
 
+def test_resize_vertical_up_horizontal_down(gpu, monkeypatch):
+    """A vertical upscale combined with a horizontal downscale (or any upscale whose 4-column groups touch more than 8
+    source pixels): the upscaling kernel's wide-window variant (kernel 7, csrc/resize_up.cuh WPX = 0) -- every channel
+    count and depth, widths that are not multiples of a tile or of 4, windows up to the 64-pixel cap; past the cap, and
+    with the variant switched off, the bit-exact kernel serves the shape."""
+    P = gpu
+    rng = np.random.default_rng(909)
+    shapes = [("rgb", 3000, 200, 800, 600, "lanczos", 1.0), ("rgba", 2000, 150, 700, 450, "cubic", 1.0),
+              ("grey", 1777, 130, 431, 391, "mitchel", 1.0), ("greya", 1500, 140, 333, 500, "catmulrom", 1.0),
+              ("r16g16b16a16", 1200, 140, 301, 421, "lanczos", 1.0), ("r16g16b16", 1600, 131, 500, 300, "triangle", 1.0),
+              ("r16", 2048, 200, 256, 401, "cubic", 0.7), ("r16g16", 900, 130, 450, 390, "box", 1.0),
+              ("rgb", 1000, 300, 980, 700, "lanczos", 1.5), ("rgba", 4000, 150, 500, 160, "triangle", 1.0)]
+    for (pixel, sw, sh, dw, dh, filt, fw) in shapes:
+        img = rand_image(rng, sw, sh, pixel)
+        want = oracle_resize(img, dw, dh, filt, fw)
+        got = P.resizeSync(img, {"width": dw, "height": dh, "filter": filt, "filterScale": fw})
+        assert P.last_resize_kernel() == 7, (pixel, sw, sh, dw, dh, filt, P.last_resize_kernel())
+        assert_resize_close(got, want, False, ("wide-up", pixel, sw, sh, dw, dh, filt, fw))
+    img = rand_image(rng, 3000, 200, "rgb")
+    want = oracle_resize(img, 800, 600, "lanczos", 1.0)
+    monkeypatch.setenv("PICHA_B200_NO_WIDE_UP", "1")
+    got = P.resizeSync(img, {"width": 800, "height": 600, "filter": "lanczos"})
+    monkeypatch.delenv("PICHA_B200_NO_WIDE_UP")
+    assert P.last_resize_kernel() == 1 and got.equalPixels(want)
+    img = rand_image(rng, 6000, 140, "rgb")            # 15:1 lanczos: 4 columns span more than 64 source pixels
+    want = oracle_resize(img, 400, 300, "lanczos", 1.0)
+    got = P.resizeSync(img, {"width": 400, "height": 300, "filter": "lanczos"})
+    assert P.last_resize_kernel() == 1 and got.equalPixels(want)
+
+
 def test_resize_column_pass_bank_groups(gpu):
     """The downscaling kernel's horizontal pass by columns (pass2_cols) deals a tile's columns to lanes by the
     16-byte bank group their tap window starts in.  Ratios that put EVERY window into the same group (windows 32
@@ -401,9 +431,10 @@ def test_resize_ill_conditioned_filters_take_the_exact_kernel(gpu):
     img = rand_image(rng, 588, 1301, "r16g16b16a16")
     P.resizeSync(img, {"width": 187, "height": 420, "filter": "catmulrom"})
     assert P.last_resize_kernel() != 1
-    # (a vertical upscale with a horizontal downscale has no throughput kernel of its own: bit-exact kernel)
-    P.resizeSync(img, {"width": 187, "height": 2849, "filter": "catmulrom"})
-    assert P.last_resize_kernel() == 1
+    # (a vertical upscale with a horizontal downscale: the upscaling kernel's wide-window variant)
+    got = P.resizeSync(img, {"width": 187, "height": 2849, "filter": "catmulrom"})
+    assert P.last_resize_kernel() == 7
+    assert_resize_close(got, oracle_resize(img, 187, 2849, "catmulrom", 1.0), False, "wide-up, well conditioned")
 
 
 def axis_matrix(filt, fw, src, dst, vertical):
