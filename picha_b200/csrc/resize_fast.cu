@@ -269,7 +269,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 		ul.ua.win_bytes = (win_px * bpp + 15) & ~15;
 		ul.ua.hscale = std::ldexp(1.0f, up::kHExp);
 		ul.ua.fuse = fuse;
-		if (up::smem_bytes(ul.ua.win_bytes) > max_dynamic_smem()) use_up = false;
+		if (up::smem_bytes(ul.ua.win_bytes, wide) > max_dynamic_smem()) use_up = false;
 	}
 	// The generic kernel is not a default route any more: shapes neither specialised kernel takes (vertical depth
 	// above 8; a vertical upscale with a horizontal downscale; misaligned destinations of upscales) get the bit-exact
@@ -329,7 +329,7 @@ cudaError_t launch_resize_fast(const DevBatch &src, const DevBatch &dst, int n, 
 			dl.group = 4;
 		}
 	}
-	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes) : use_down && dl.da.rq > 0 ? down::smem_layout_int(dl.da.rq * dl.da.dx).total
+	const int smem_total = use_up ? up::smem_bytes(ul.ua.win_bytes, ul.wpx == 0) : use_down && dl.da.rq > 0 ? down::smem_layout_int(dl.da.rq * dl.da.dx).total
 	                       : use_down ? down::smem_layout(dl.group, t.tile_w, bpp, channels, dl.da.nb, dl.da.wrows, dl.da.direct != 0, dl.threads, down::by_columns(channels, dl.group)).total
 	                                : smem_layout(deep, t.tile_w, bpp, t.xstride).total;
 	if (smem_total > max_dynamic_smem()) return cudaErrorNotSupported;

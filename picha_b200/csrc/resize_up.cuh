@@ -48,6 +48,8 @@ constexpr int NPX = 4;        // output pixels per thread
 constexpr int TILE = NT * NPX;   // output pixels per tile
 constexpr int NS = 3;         // ring stages
 constexpr int RS = 8;         // source rows per stage
+constexpr int RS_WIDE = 2;    // the same for the wide-window variant: its rows are ten times the work and several times
+                              // the bytes, so a shallow ring keeps 6 CTAs per SM (8-row stages: 3)
 constexpr int kHExp = 120;    // horizontal weights are scaled by 2^kHExp
 constexpr int kMaxDepth = 6;
 
@@ -58,7 +60,7 @@ struct UpArgs {
 	FuseArgs fuse;     // resize, then convert: the pack stage stores the destination's pixel format
 };
 
-__host__ __device__ inline int smem_bytes(int win_bytes) { return NS * RS * win_bytes + 2 * NS * 8; }
+__host__ __device__ inline int smem_bytes(int win_bytes, bool wide = false) { return NS * (wide ? RS_WIDE : RS) * win_bytes + 2 * NS * 8; }
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -71,6 +73,7 @@ struct RingState {
 };
 
 // One stage: the rows [row0, row0 + RS) that exist and belong to the band, copy_bytes of each.
+template <int RS>
 __device__ __forceinline__ void issue_stage(uint32_t dst, uint32_t bar, const uint8_t *src, long long stride, int row0,
                                             int row_end, int win_bytes, int copy_bytes) {
 	int rows = row_end - row0;
@@ -93,6 +96,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 	// registers per staged pixel: 4-channel pixels travel as 32-bit words, the others as one zero-extended value each
 	constexpr int WPP = C == 4 ? (DEEP ? 2 : 1) : C;
 	constexpr bool WIDE = WPX_ == 0;             // the wide-window variant: no register block of weights, no raw-pixel prefetch
+	constexpr int RS = WIDE ? RS_WIDE : up::RS;  // source rows per ring stage
 	constexpr int WPX = WIDE ? 1 : WPX_;
 	const int tid = threadIdx.x;
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -123,7 +127,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
 		for (int k = 0; k < NS; ++k)
-			if (k < rs.nstages) issue_stage(ring + k * stage_bytes, bars + 8 * k, simg, src.stride, rlo + k * RS, rhi + 1, ua.win_bytes, copy_bytes);
+			if (k < rs.nstages) issue_stage<RS>(ring + k * stage_bytes, bars + 8 * k, simg, src.stride, rlo + k * RS, rhi + 1, ua.win_bytes, copy_bytes);
 	}
 
 	// ---- this thread's four output pixels: window start and dense weight block ---------------------
@@ -177,7 +181,7 @@ resize_up_kernel(DevBatch src, DevBatch dst, FastTables t, const __grid_constant
 					"mbarrier.pending_count.b64 %0, st;\n\t}"
 					: "=r"(pending) : "r"(bars + 8 * (NS + prev)) : "memory");
 				if (pending == 1)
-					issue_stage(ring + prev * stage_bytes, bars + 8 * prev, simg, src.stride, rlo + (rs.stage + NS) * RS, rhi + 1,
+					issue_stage<RS>(ring + prev * stage_bytes, bars + 8 * prev, simg, src.stride, rlo + (rs.stage + NS) * RS, rhi + 1,
 					            ua.win_bytes, copy_bytes);
 			}
 		}
@@ -430,7 +434,7 @@ struct UpLaunch {
 
 template <int DEPTH, bool DEEP, int WPX, int C, bool FUSED> cudaError_t launch_one(const UpLaunch &a) {
 	auto kern = resize_up_kernel<DEPTH, DEEP, WPX, C, FUSED>;
-	const int smem_total = smem_bytes(a.ua.win_bytes);
+	const int smem_total = smem_bytes(a.ua.win_bytes, WPX == 0);
 	static SmemGrant granted;   // (per instantiation: see grow_dynamic_smem)
 	cudaError_t e = grow_dynamic_smem(reinterpret_cast<const void *>(kern), smem_total, &granted);
 	if (e != cudaSuccess) return e;
