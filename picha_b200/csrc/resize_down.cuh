@@ -17,11 +17,14 @@
 //   * Accumulator slots are fixed (output row y lives in slot y % DEPTH) and the host lays the
 //     weights of a source row out in slot order: the row body is the same code for every row --
 //     no rotation by unrolling, no per-row branches; only the (rare) emit picks a slot.
-//   * The row loop counts down to the next event (an output row completes, or the ring stage
-//     ends) in one counter; rows are prefetched one ahead into alternating registers.
+//   * The row loop decides nothing by arithmetic: the host puts a flag word behind every source row's weights (how
+//     many outputs the row completes, whether the ring stage ends with the next row).  Per emit slot there are two
+//     row bodies -- the first row after an emit, which clears the slot on the way, and one loop body -- because the
+//     row loop's code is what fills the instruction cache.
 //   * Ring stages are handed back through `empty` mbarriers (no CTA-wide barrier in pass 1).
-//   * Pass 2 uses packed FMAs (fma.rn.f32x2: two channels per instruction, weights stored
-//     duplicated in shared memory) and stores 4- and 8-byte pixels straight to global memory.
+//   * Pass 2 comes in four forms: by columns (pass2_cols: 1-, 3-, 4-channel pixels), general
+//     (pass2: 2-channel pixels, 8-row groups), integer ratios of 4-channel pixels (pass2_int4), and each of them
+//     converting (FUSED); all store pixels straight to global memory where the destination's alignment allows.
 #ifndef PICHA_B200_RESIZE_DOWN_CUH
 #define PICHA_B200_RESIZE_DOWN_CUH
 
