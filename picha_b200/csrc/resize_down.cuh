@@ -1005,149 +1005,164 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	int gcount = 0;
 	auto flags = [](const float (&w)[DEPTH + 1]) { return (int)__float_as_uint(w[DEPTH]); };
 	bool done = y >= y1;
+	// The pieces of the row loop (lambdas, inlined where they are used):
+	// the first row after the emit of slot `fresh`: clears that slot on the way (see body; at the band's start the slot
+	// is zero anyway); the row after it moves to ra whatever the flags say
+	auto first_row = [&](const int fresh) {
+		load_row(rb);
+		load_w(wb, widx);
+		widx += WS;
+		body(fresh, ra, wa);
+		const int f = flags(wa);
+#pragma unroll
+		for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+		for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+		if (f) {
+			if (f & kEvStage) advance();
+			pending = f & kEvCount;
+		}
+	};
+	// the rows after it, until one completes an output
+	auto rest_rows = [&]() {
+#if PICHA_DOWN_ONE_BODY
+		// (one body per loop: ptxas keeps the row and its successor in the same registers anyway -- each word of
+		// the next row is loaded right behind the last use of the current one -- so a loop unrolled over two
+		// row buffers only doubles the code, and the row loop's code is what fills the instruction cache)
+		for (;;) {
+			load_row(rb);
+			load_w(wb, widx);
+			widx += WS;
+			body(-1, ra, wa);
+			const int f = flags(wa);
+#pragma unroll
+			for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+			for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+			if (f) {
+				if (f & kEvStage) advance();
+				pending = f & kEvCount;
+				if (pending) break;
+			}
+		}
+#else
+		for (;;) {
+			load_row(rb);
+			load_w(wb, widx);
+			widx += WS;
+			body(-1, ra, wa);
+			int f = flags(wa);
+			if (f) {
+				// (rare path: once per output and once per ring stage) continue with the current row in ra
+#pragma unroll
+				for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
+#pragma unroll
+				for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
+				if (f & kEvStage) advance();
+				pending = f & kEvCount;
+				if (pending) break;
+				continue;
+			}
+			load_row(ra);
+			load_w(wa, widx);
+			widx += WS;
+			body(-1, rb, wb);
+			f = flags(wb);
+			if (f) {
+				if (f & kEvStage) advance();
+				pending = f & kEvCount;
+				if (pending) break;
+			}
+		}
+#endif
+	};
+	// emit: slot S is final; it becomes the slot of output y + DEPTH
+	auto emit = [&](const int S) {
+#ifdef PICHA_DOWN_SKIP_EMIT      // (timing experiments only)
+		if (y >= y0) ++gcount;
+		if (y == -12345)
+#endif
+		{
+			// (predicated stores, no branch: around a branch ptxas renames the slot's registers and moves them back)
+			const uint32_t keep = y >= y0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t addr = P2 == 1 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR, NTT) * 4) + q * (16 * NTT);
+				asm volatile(
+					"{\n\t.reg .pred p;\n\t"
+					"setp.ne.u32 p, %3, 0;\n\t"
+					"@p st.shared.v2.b64 [%0], {%1, %2};\n\t}"
+					::"r"(addr), "l"(acc[S][2 * q]), "l"(acc[S][2 * q + 1]), "r"(keep) : "memory");
+			}
+			gcount += keep;
+		}
+		// The slot is cleared by the next row's body (see `fresh`); only when another output follows without a row
+		// in between (the discarded outputs at a band's start, ratios below 1 row per output) is it zeroed here --
+		// in place (tied operand, x * 0): a plain "= 0" makes new values that ptxas pairs up for CS2R and then
+		// shuffles every accumulator of the kernel between two register assignments per output row.
+		if (!PICHA_DOWN_FRESH || pending != 1) {
+#pragma unroll
+			for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[S][i]) : "l"(0ull));
+		}
+	};
+	// a group of GR output rows is complete (or the band ends): the horizontal pass
+	auto group = [&]() {
+		if (gcount == GR || (done && gcount > 0)) {
+			uint8_t *const gbase = dtile + (long long)(y - gcount) * dst.stride;
+#ifndef PICHA_DOWN_SKIP_SYNC     // (timing experiments only)
+			__syncthreads();           // the group's intermediate rows are complete
+#endif
+#ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
+			if constexpr (P2 == 1) {
+				Pass2IntArgs pi;
+				pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
+				pi.c0 = da.rq * x0 + da.off0 - sx0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
+				pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
+				pi.fuse = da.fuse;
+				pi.ng = gcount;
+				pi.gbase = gbase;
+				pass2_int4_any<DEEP, FUSED>(pi, da.rq, da.dx);
+			} else {
+				Pass2Args pa;
+				pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
+				pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
+				pa.fuse = da.fuse;
+				pa.ng = gcount;
+				pa.gbase = gbase;
+				if constexpr (P2 == 2) {
+					pa.xf = L.xslots;
+					pa.nslots = nslots;
+					pass2_cols<C, DEEP, GR, FUSED, NTT>(pa);
+				} else {
+					pass2<C, DEEP, GR, FUSED, NTT>(pa);
+				}
+			}
+#endif
+#ifndef PICHA_DOWN_SKIP_SYNC
+			__syncthreads();           // pass 1 may overwrite the intermediate rows again
+#endif
+			gcount = 0;
+		}
+	};
+	// (One copy of the loop body and of the group code for ALL slots, the slot-specific pieces hanging off a uniform
+	// counter, halves the loop's code once more and is 9 % slower: the compare chain in front of the first row and of
+	// the emit sits on every output's critical path -- profiles/r02_ablation.txt, "shared1".)
 	while (!done) {
 #pragma unroll
 		for (int s = 0; s < DEPTH; ++s) {
 			if (done) break;
 			if (pending == 0) {
 #if PICHA_DOWN_FRESH
-				// The first row after the emit of slot s - 1 clears that slot on the way (`fresh` in body; at the
-				// band's start the slot is zero anyway).  Peeled, so that the slot is static; the row after it moves
-				// to ra whatever the flags say, and the loop below starts where it always did.
-				{
-					load_row(rb);
-					load_w(wb, widx);
-					widx += WS;
-					body((s + DEPTH - 1) % DEPTH, ra, wa);
-					const int f = flags(wa);
-#pragma unroll
-					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
-#pragma unroll
-					for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
-					if (f) {
-						if (f & kEvStage) advance();
-						pending = f & kEvCount;
-					}
-				}
+				first_row((s + DEPTH - 1) % DEPTH);
 				if (pending == 0)
 #endif
-#if PICHA_DOWN_ONE_BODY
-				// (one body per loop: ptxas keeps the row and its successor in the same registers anyway -- each word of
-				// the next row is loaded right behind the last use of the current one -- so a loop unrolled over two
-				// row buffers only doubles the code, and the row loop's code is what fills the instruction cache)
-				for (;;) {
-					load_row(rb);
-					load_w(wb, widx);
-					widx += WS;
-					body(-1, ra, wa);
-					const int f = flags(wa);
-#pragma unroll
-					for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
-#pragma unroll
-					for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
-					if (f) {
-						if (f & kEvStage) advance();
-						pending = f & kEvCount;
-						if (pending) break;
-					}
-				}
-#else
-				for (;;) {
-					load_row(rb);
-					load_w(wb, widx);
-					widx += WS;
-					body(-1, ra, wa);
-					int f = flags(wa);
-					if (f) {
-						// (rare path: once per output and once per ring stage) continue with the current row in ra
-#pragma unroll
-						for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
-#pragma unroll
-						for (int j = 0; j <= DEPTH; ++j) wa[j] = wb[j];
-						if (f & kEvStage) advance();
-						pending = f & kEvCount;
-						if (pending) break;
-						continue;
-					}
-					load_row(ra);
-					load_w(wa, widx);
-					widx += WS;
-					body(-1, rb, wb);
-					f = flags(wb);
-					if (f) {
-						if (f & kEvStage) advance();
-						pending = f & kEvCount;
-						if (pending) break;
-					}
-				}
-#endif
+				rest_rows();
 			}
-			// emit: slot s is final; it becomes the slot of output y + DEPTH
-#ifdef PICHA_DOWN_SKIP_EMIT      // (timing experiments only)
-			if (y >= y0) ++gcount;
-			if (y == -12345)
-#endif
-			{
-				// (predicated stores, no branch: around a branch ptxas renames the slot's registers and moves them back)
-				const uint32_t keep = y >= y0;
-#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					const uint32_t addr = P2 == 1 ? epos[q] + gcount * kIntRowBytes : my_tmp + gcount * (tmps(C, GR, NTT) * 4) + q * (16 * NTT);
-					asm volatile(
-						"{\n\t.reg .pred p;\n\t"
-						"setp.ne.u32 p, %3, 0;\n\t"
-						"@p st.shared.v2.b64 [%0], {%1, %2};\n\t}"
-						::"r"(addr), "l"(acc[s][2 * q]), "l"(acc[s][2 * q + 1]), "r"(keep) : "memory");
-				}
-				gcount += keep;
-			}
-			// The slot is cleared by the next row's body (see `fresh`); only when another output follows without a row
-			// in between (the discarded outputs at a band's start, ratios below 1 row per output) is it zeroed here --
-			// in place (tied operand, x * 0): a plain "= 0" makes new values that ptxas pairs up for CS2R and then
-			// shuffles every accumulator of the kernel between two register assignments per output row.
-			if (!PICHA_DOWN_FRESH || pending != 1) {
-#pragma unroll
-				for (int i = 0; i < NV / 2; ++i) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(acc[s][i]) : "l"(0ull));
-			}
+			emit(s);
 			--pending;
 			++y;
 			done = y >= y1;
-			if (gcount == GR || (done && gcount > 0)) {
-				uint8_t *const gbase = dtile + (long long)(y - gcount) * dst.stride;
-#ifndef PICHA_DOWN_SKIP_SYNC     // (timing experiments only)
-				__syncthreads();           // the group's intermediate rows are complete
-#endif
-#ifndef PICHA_DOWN_SKIP_P2       // (timing experiments only: pass 1 and its events without the horizontal pass)
-				if constexpr (P2 == 1) {
-					Pass2IntArgs pi;
-					pi.row0 = sbase + LI.tmp + kIntGuard; pi.wtab = sbase + LI.wtab; pi.dstride = dst.stride; pi.tw = tw; pi.tid = tid;
-					pi.c0 = da.rq * x0 + da.off0 - sx0; pi.blk0 = x0 / kIntU; pi.nl = da.nl; pi.br0 = da.br0;
-					pi.vec = ((reinterpret_cast<uintptr_t>(dtile) | (uintptr_t)dst.stride) & 15) == 0;
-					pi.fuse = da.fuse;
-					pi.ng = gcount;
-					pi.gbase = gbase;
-					pass2_int4_any<DEEP, FUSED>(pi, da.rq, da.dx);
-				} else {
-					Pass2Args pa;
-					pa.sbase = sbase; pa.tmp = L.tmp; pa.xw = L.xw; pa.xf = L.xf; pa.outt = L.out;
-					pa.xs2 = L.xs2; pa.out_stride = L.out_stride; pa.dstride = dst.stride; pa.tw = tw; pa.tid = tid; pa.direct = direct; pa.nb = da.nb;
-					pa.fuse = da.fuse;
-					pa.ng = gcount;
-					pa.gbase = gbase;
-					if constexpr (P2 == 2) {
-						pa.xf = L.xslots;
-						pa.nslots = nslots;
-						pass2_cols<C, DEEP, GR, FUSED, NTT>(pa);
-					} else {
-						pass2<C, DEEP, GR, FUSED, NTT>(pa);
-					}
-				}
-#endif
-#ifndef PICHA_DOWN_SKIP_SYNC
-				__syncthreads();           // pass 1 may overwrite the intermediate rows again
-#endif
-				gcount = 0;
-			}
+			group();
 		}
 	}
 
