@@ -257,7 +257,7 @@ void build_wide_blocks(const FastAxisX &x, int dst_size, int cap, float scale, W
 			window = std::max(window, x.first[px] + x.count[px] - lo);
 		}
 	}
-	if (window <= 0 || window > cap) return;
+	if (window <= 8 || window > cap) return;         // (up to 8 pixels the kernel keeps the block in registers: no table)
 	out.window = window;
 	out.w.assign((size_t)groups * window * 4, 0.0f);
 	for (int g = 0; g < groups; ++g) {

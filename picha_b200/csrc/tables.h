@@ -88,7 +88,8 @@ void build_flat_rows(const FastAxisX &x, int channels, FlatRows &out);
 // Upscaling kernel, wide-window variant (csrc/resize_up.cuh, WPX = 0): a thread owns 4 consecutive output columns and
 // walks the source pixels [first[4g], first[4g] + window) of every row; block g holds, for each of those pixels, the
 // weight it carries into each of the 4 columns (zero where it is not one of the column's taps), scaled by `scale`.
-// window = 0: no such table (some group's pixels do not start at its first column's, or the widest group exceeds cap).
+// window = 0: no such table (some group's pixels do not start at its first column's, the widest group exceeds cap, or
+// no group spans more than the 8 pixels the regular variant handles from registers).
 struct WideBlocks {
 	int window = 0;
 	std::vector<float> w;   // [(dst + 3) / 4][window][4]
