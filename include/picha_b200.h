@@ -215,6 +215,14 @@ int picha_b200_contribs(int filter_tag, float filter_width, int srcsize, int dst
                         int *left, int *count, int *offset,
                         float *weights, int *eff_row, int cap);
 
+/* The dense weight blocks of the upscaling kernel's wide-window variant for one horizontal axis (csrc/tables.h:
+ * WideBlocks; a host-side table, no device needed): block g = output columns 4g .. 4g+3 holds, for each of the
+ * `window` source pixels from the first tap of column 4g on, the weight that pixel carries into each of the 4 columns
+ * (unscaled here; 0 where it is not one of the column's taps).  Returns the window (source pixels per block), 0 if
+ * this axis has no such table (no block spans more than 8 pixels, or some block more than 64), or a negative status;
+ * blocks receives (dstsize + 3) / 4 * window * 4 floats if it holds at least cap of them. */
+int picha_b200_wide_blocks(int filter_tag, float filter_width, int srcsize, int dstsize, float *blocks, int cap);
+
 #ifdef __cplusplus
 }
 #endif

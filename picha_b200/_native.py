@@ -90,6 +90,7 @@ SIGNATURES = {
                                                         ctypes.c_uint64, ctypes.c_void_p]),
     "picha_b200_contribs": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, _ip, _ip, _ip,
                                            _fp, _ip, ctypes.c_int]),
+    "picha_b200_wide_blocks": (ctypes.c_int, [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, _fp, ctypes.c_int]),
 }
 
 

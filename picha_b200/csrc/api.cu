@@ -1072,4 +1072,20 @@ int picha_b200_contribs(int filter_tag, float filter_width, int srcsize, int dst
 	return n;
 }
 
+int picha_b200_wide_blocks(int filter_tag, float filter_width, int srcsize, int dstsize, float *blocks, int cap) {
+	if (filter_tag < 0 || filter_tag >= PICHA_B200_NUM_FILTERS) return PICHA_B200_ERR_INVALID_FILTER;
+	if (filter_width != filter_width || filter_width <= 0) return PICHA_B200_ERR_INVALID_FILTER_WIDTH;
+	if (srcsize <= 0 || dstsize <= 0) return PICHA_B200_ERR_INVALID_DIMENSIONS;
+	AxisTable t;
+	build_axis(filter_tag, filter_width, srcsize, dstsize, t);
+	FastAxisX fx;
+	build_fast_x(t, fx);
+	WideBlocks wide;
+	build_wide_blocks(fx, dstsize, 64, 1.0f, wide);
+	const int n = (int)wide.w.size();
+	if (blocks && cap >= n)
+		for (int i = 0; i < n; ++i) blocks[i] = wide.w[i];
+	return wide.window;
+}
+
 }  // extern "C"

@@ -318,3 +318,46 @@ def test_batch_plan_chunks_same_shape_runs():
     chunks = plan_batch(srcs, dsts, lanes=1)
     assert chunks == [(0, 5), (5, 1), (6, 2), (8, 2)]
     assert plan_batch([], []) == []
+
+
+def test_wide_blocks_are_the_contribution_table_regrouped():
+    """Host table of the upscaling kernel's wide-window variant (csrc/tables.cc: build_wide_blocks): block g lists, for
+    the source pixels from column 4g's first tap on, the weight each carries into columns 4g .. 4g+3.  Regrouped by
+    column it must be the reference's contribution table again (taps below 2^-30, which the fast-path tables prune,
+    may be missing); axes whose blocks span at most 8 pixels, or more than 64, have no table."""
+    import ctypes
+    ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+    for filt, fw, src, dst in [("lanczos", 1.0, 3000, 800), ("cubic", 0.7, 1777, 431), ("box", 1.3, 3745, 703),
+                               ("triangle", 1.0, 999, 334), ("mitchel", 2.0, 640, 600)]:
+        f = N.FILTERS.index(filt)
+        window = N.lib.picha_b200_wide_blocks(f, fw, src, dst, None, 0)
+        assert 8 < window <= 64, (filt, src, dst, window)
+        groups = (dst + 3) // 4
+        blocks = np.zeros(groups * window * 4, np.float32)
+        assert N.lib.picha_b200_wide_blocks(f, fw, src, dst, blocks.ctypes.data_as(fp), blocks.size) == window
+        blocks = blocks.reshape(groups, window, 4)
+        left = np.zeros(dst, np.int32); count = np.zeros(dst, np.int32); off = np.zeros(dst, np.int32)
+        n = N.lib.picha_b200_contribs(f, fw, src, dst, left.ctypes.data_as(ip), count.ctypes.data_as(ip), off.ctypes.data_as(ip), None, None, 0)
+        w = np.zeros(n, np.float32)
+        N.lib.picha_b200_contribs(f, fw, src, dst, left.ctypes.data_as(ip), count.ctypes.data_as(ip), off.ctypes.data_as(ip),
+                                  w.ctypes.data_as(fp), None, n)
+        dense = np.zeros((dst, src), np.float32)
+        for x in range(dst):
+            dense[x, left[x]:left[x] + count[x]] = w[off[x]:off[x] + count[x]]
+        for g in range(groups):
+            # the block starts at the first tap of column 4g that survives the pruning
+            taps = np.nonzero(np.abs(dense[4 * g]) >= 2.0 ** -30)[0]
+            lo = int(taps[0])
+            for p in range(4):
+                x = 4 * g + p
+                got = np.zeros(src + window, np.float32)
+                got[lo:lo + window] = blocks[g, :, p]
+                if x >= dst:
+                    assert not got.any()
+                    continue
+                want = np.where(np.abs(dense[x]) >= 2.0 ** -30, dense[x], 0)
+                assert np.array_equal(got[:src], want), (filt, src, dst, x)
+    # a plain 2x upscale keeps its blocks in registers (no table); a 20:1 lanczos downscale exceeds the window
+    assert N.lib.picha_b200_wide_blocks(N.FILTERS.index("mitchel"), 1.0, 500, 1000, None, 0) == 0
+    assert N.lib.picha_b200_wide_blocks(N.FILTERS.index("lanczos"), 1.0, 8000, 400, None, 0) == 0
+
