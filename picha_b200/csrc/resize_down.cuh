@@ -75,6 +75,9 @@ __host__ __device__ constexpr int box_bytes(bool deep, int nt) { return (deep ? 
 #ifndef PICHA_DOWN_ONE_BODY
 #define PICHA_DOWN_ONE_BODY 1    // 0: the row loop unrolled over two row buffers (for A/B builds)
 #endif
+#ifndef PICHA_DOWN_SPLIT_LOAD
+#define PICHA_DOWN_SPLIT_LOAD 1    // 0: the whole next row is loaded in front of the body (for A/B builds)
+#endif
 #ifndef PICHA_DOWN_COLS
 #define PICHA_DOWN_COLS 2        // horizontal pass by columns: 2 every channel count, 1 odd ones only, 0 never (for A/B builds)
 #endif
@@ -902,19 +905,18 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// lanes read consecutive words and, in the emit, write consecutive float4s: no bank conflicts).
 	const uint32_t thread_off = DEEP ? 8 * tid : 4 * tid;
 	uint32_t faddr = 0;     // shared address of this thread's first chunk in the next row to fetch
-	auto load_row = [&](uint32_t (&w)[WPT]) {
-		// chunk q = values 4 * (tid + NTT * q) ...; rows of two boxes hold chunks 0, 1 in the first and 2, 3 in the second
+	// chunk q = values 4 * (tid + NTT * q) ...; rows of two boxes hold chunks 0, 1 in the first and 2, 3 in the second
+	auto load_chunk = [&](uint32_t (&w)[WPT], const int q) {
 		if (DEEP) {
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const uint2 v = lds<uint2>(faddr + (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2));
-				w[(2 * q) % WPT] = v.x; w[(2 * q + 1) % WPT] = v.y;
-			}
+			const uint2 v = lds<uint2>(faddr + (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2));
+			w[(2 * q) % WPT] = v.x; w[(2 * q + 1) % WPT] = v.y;
 		} else {
-#pragma unroll
-			for (int q = 0; q < 4; ++q)
-				w[q % WPT] = (uint32_t)lds<int>(faddr + (BOXES == 2 ? (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2) : q * (BOXB / 4)));
+			w[q % WPT] = (uint32_t)lds<int>(faddr + (BOXES == 2 ? (q >> 1) * (RSK * BOXB) + (q & 1) * (BOXB / 2) : q * (BOXB / 4)));
 		}
+	};
+	auto load_row = [&](uint32_t (&w)[WPT]) {
+#pragma unroll
+		for (int q = 0; q < 4; ++q) load_chunk(w, q);
 		faddr += BOXB;
 	};
 	auto advance = [&]() {
@@ -1009,10 +1011,21 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 	// the first row after the emit of slot `fresh`: clears that slot on the way (see body; at the band's start the slot
 	// is zero anyway); the row after it moves to ra whatever the flags say
 	auto first_row = [&](const int fresh) {
+#if PICHA_DOWN_SPLIT_LOAD
+		load_chunk(rb, 0);
+		load_chunk(rb, 1);
+		load_w(wb, widx);
+		widx += WS;
+		body(fresh, ra, wa);
+		load_chunk(rb, 2);
+		load_chunk(rb, 3);
+		faddr += BOXB;
+#else
 		load_row(rb);
 		load_w(wb, widx);
 		widx += WS;
 		body(fresh, ra, wa);
+#endif
 		const int f = flags(wa);
 #pragma unroll
 		for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
@@ -1030,10 +1043,23 @@ resize_down_kernel(const CUtensorMap *__restrict__ smap, DevBatch dst, FastTable
 		// the next row is loaded right behind the last use of the current one -- so a loop unrolled over two
 		// row buffers only doubles the code, and the row loop's code is what fills the instruction cache)
 		for (;;) {
+#if PICHA_DOWN_SPLIT_LOAD
+			// (the next row's first two chunks before the body, its last two behind it: ptxas hoists loads issued
+			// before the body above the last use of the registers they will end up in, and pays two MOVs per row)
+			load_chunk(rb, 0);
+			load_chunk(rb, 1);
+			load_w(wb, widx);
+			widx += WS;
+			body(-1, ra, wa);
+			load_chunk(rb, 2);
+			load_chunk(rb, 3);
+			faddr += BOXB;
+#else
 			load_row(rb);
 			load_w(wb, widx);
 			widx += WS;
 			body(-1, ra, wa);
+#endif
 			const int f = flags(wa);
 #pragma unroll
 			for (int i = 0; i < WPT; ++i) ra[i] = rb[i];
